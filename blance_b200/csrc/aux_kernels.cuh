@@ -1,0 +1,255 @@
+// blance_b200/csrc/aux_kernels.cuh — the data-parallel kernels around the
+// sequential assign pass: row filtering, weighted node histogram, partition sort
+// keys, convergence compare/commit, row (un)packing, and CalcPartitionMoves.
+// All are one-thread-per-partition, HBM-streaming kernels over the pooled arrays
+// (see device_types.cuh); grids are sized as multiples of the SM count by the host.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "blance_b200.h"
+#include "device_types.cuh"
+
+namespace blance_dev {
+
+// ---- H2D side: caller layout -> device layout -----------------------------------------
+// rows [PU][SL] -> [PU][SLP] (padded with NO_NODE); shapes uint8[PU][S] -> 2-bit fields.
+__global__ void k_unpack(DPool pool, const int32_t* __restrict__ raw_cur, const int32_t* __restrict__ raw_prev,
+                         const uint8_t* __restrict__ cur_shape, const uint8_t* __restrict__ prev_shape,
+                         const long long* __restrict__ raw_rows_off, const long long* __restrict__ raw_shape_off,
+                         long long n_parts_total) {
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n_parts_total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const DInst& D = pool.insts[pool.part_inst[g]];
+    const long long lp = g - D.part_off;
+    const int32_t* rc = raw_cur + raw_rows_off[pool.part_inst[g]] + lp * D.SL;
+    const int32_t* rp = raw_prev + raw_rows_off[pool.part_inst[g]] + lp * D.SL;
+    int32_t* dc = pool.rows + D.rows_off + lp * D.SLP;
+    int32_t* dp = pool.prev_rows + D.rows_off + lp * D.SLP;
+    for (int i = 0; i < D.SLP; ++i) {
+      dc[i] = i < D.SL ? rc[i] : BLANCE_NO_NODE;
+      dp[i] = i < D.SL ? rp[i] : BLANCE_NO_NODE;
+    }
+    const uint8_t* sc = cur_shape + raw_shape_off[pool.part_inst[g]] + lp * D.S;
+    const uint8_t* sp = prev_shape + raw_shape_off[pool.part_inst[g]] + lp * D.S;
+    uint32_t mc = 0, mp = 0;
+    for (int s = 0; s < D.S; ++s) { mc |= (uint32_t)(sc[s] & 3u) << (2 * s); mp |= (uint32_t)(sp[s] & 3u) << (2 * s); }
+    pool.pmeta[g] = mc;
+    pool.prev_meta[g] = mp;
+  }
+}
+
+// ---- D2H side: device layout -> caller layout -------------------------------------------
+__global__ void k_pack(DPool pool, int32_t* __restrict__ raw_next, uint8_t* __restrict__ next_shape,
+                       uint8_t* __restrict__ warn, const long long* __restrict__ raw_rows_off,
+                       const long long* __restrict__ raw_shape_off, long long n_parts_total) {
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n_parts_total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int inst = pool.part_inst[g];
+    const DInst& D = pool.insts[inst];
+    const long long lp = g - D.part_off;
+    const int32_t* src = pool.rows + D.rows_off + lp * D.SLP;
+    int32_t* dst = raw_next + raw_rows_off[inst] + lp * D.SL;
+    for (int i = 0; i < D.SL; ++i) dst[i] = src[i];
+    const uint32_t m = pool.pmeta[g];
+    uint8_t* ds = next_shape + raw_shape_off[inst] + lp * D.S;
+    uint8_t* dw = warn + raw_shape_off[inst] + lp * D.S;
+    for (int s = 0; s < D.S; ++s) { ds[s] = (uint8_t)meta_shape(m, s); dw[s] = (uint8_t)((m >> (16 + s)) & 1u); }
+  }
+}
+
+// ---- start of an iteration (plan.go:83-88, 70) -------------------------------------------
+// Working rows = partitionsToAssign rows minus the to-be-removed nodes (order kept);
+// every present state list becomes a non-nil slice; warnings are reset.
+__global__ void k_prepare_rows(DPool pool, long long n_parts_total) {
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n_parts_total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const DInst& D = pool.insts[pool.part_inst[g]];
+    if (!D.active || !(pool.pflags[g] & PF_IN_ASSIGN)) continue;
+    int32_t* row = pool.rows + D.rows_off + (g - D.part_off) * D.SLP;
+    uint32_t m = pool.pmeta[g] & 0xFFFFu;          // drop the warn bits of the previous iteration
+    for (int s = 0; s < D.S; ++s) {
+      if (meta_shape(m, s) == BLANCE_SHAPE_ABSENT) continue;
+      m = meta_set_shape(m, s, BLANCE_SHAPE_LIST);
+      if (!D.rm_active) continue;
+      int o = D.state_slot_off[s];
+      const int hi = D.state_slot_off[s + 1];
+      for (int i = o; i < hi; ++i) {
+        const int32_t x = row[i];
+        if (x == BLANCE_NO_NODE) break;
+        if (!pool.node_removed[D.nodeid_off + x]) row[o++] = x;
+      }
+      for (; o < hi; ++o) row[o] = BLANCE_NO_NODE;
+    }
+    pool.pmeta[g] = m;
+  }
+}
+
+// ---- countStateNodes (plan.go:374-399) over ALL of prevMap ---------------------------------
+// Weighted histogram state x node.  SMEM_PRIV: one instance whose S*N table fits in
+// shared memory -> per-CTA private histogram, flushed once (keeps 3M atomics off L2).
+template <bool SMEM_PRIV>
+__global__ void k_count_prev(DPool pool, long long n_parts_total) {
+  extern __shared__ int32_t hist[];
+  const DInst& D0 = pool.insts[0];
+  const int table = SMEM_PRIV ? D0.S * D0.N : 0;
+  if (SMEM_PRIV) {
+    for (int i = threadIdx.x; i < table; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+  }
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n_parts_total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const DInst& D = SMEM_PRIV ? D0 : pool.insts[pool.part_inst[g]];
+    if (!D.active || !(pool.pflags[g] & PF_IN_PREV)) continue;
+    const int32_t w = (D.has_part_weights && (pool.pflags[g] & PF_HAS_WEIGHT)) ? pool.pweight[g] : 1;
+    const int32_t* row = pool.prev_rows + D.rows_off + (g - D.part_off) * D.SLP;
+    for (int s = 0; s < D.S; ++s)
+      for (int i = D.state_slot_off[s]; i < D.state_slot_off[s + 1]; ++i) {
+        const int32_t x = row[i];
+        if (x == BLANCE_NO_NODE) break;
+        if (x >= D.N) continue;                       // a name outside nodesAll: never scored
+        if (SMEM_PRIV) atomicAdd(&hist[s * D.N + x], w);
+        else atomicAdd(&pool.counts[D.counts_off + (long long)s * D.N + x], w);
+      }
+  }
+  if (SMEM_PRIV) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < table; i += blockDim.x)
+      if (hist[i]) atomicAdd(&pool.counts[D0.counts_off + i], hist[i]);
+  }
+}
+
+// ---- partitionSorter key (plan.go:519-562) ----------------------------------------------------
+// key = bucket(2) | 999999999 - weight (32) | name rank (30); partitions that are not being
+// assigned sort to the end.
+__global__ void k_build_keys(DPool pool, int s, long long n_parts_total) {
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n_parts_total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const DInst& D = pool.insts[pool.part_inst[g]];
+    pool.order_alt[g] = (int32_t)(g - D.part_off);
+    const uint8_t f = pool.pflags[g];
+    if (!D.active || s >= D.S || D.state_constraints[s] <= 0 || !(f & PF_IN_ASSIGN)) { pool.keys_alt[g] = ~0ull; continue; }
+    const int32_t* row = pool.rows + D.rows_off + (g - D.part_off) * D.SLP;
+    unsigned long long bucket = 2;
+    bool b0 = false;
+    if (D.rm_active && (f & PF_IN_PREV)) {
+      const int32_t* prow = pool.prev_rows + D.rows_off + (g - D.part_off) * D.SLP;
+      for (int i = D.state_slot_off[s]; i < D.state_slot_off[s + 1]; ++i) {
+        const int32_t x = prow[i];
+        if (x == BLANCE_NO_NODE) break;
+        b0 |= pool.node_removed[D.nodeid_off + x] != 0;
+      }
+    }
+    if (b0) bucket = 0;
+    else if (!D.add_is_nil) {
+      bool hit = false;
+      if (D.add_active)
+        for (int i = 0; i < D.SLP; ++i) {
+          const int32_t x = row[i];
+          if (x != BLANCE_NO_NODE) hit |= pool.node_added[D.nodeid_off + x] != 0;
+        }
+      if (!hit) bucket = 1;
+    }
+    const long long w = (D.has_part_weights && (f & PF_HAS_WEIGHT)) ? pool.pweight[g] : 1;
+    const unsigned long long wkey = (unsigned long long)(999999999LL - w) & 0xFFFFFFFFull;   // plan.go:539
+    pool.keys_alt[g] = (bucket << 62) | (wkey << 30) | (unsigned long long)(uint32_t)pool.name_rank[g];
+  }
+}
+
+// ---- convergence test (plan.go:36-42) -------------------------------------------------------------
+__global__ void k_compare(DPool pool, long long n_parts_total) {
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n_parts_total;
+       g += (long long)gridDim.x * blockDim.x) {
+    DInst& D = pool.insts[pool.part_inst[g]];
+    const uint8_t f = pool.pflags[g];
+    if (!D.active || !(f & PF_IN_ASSIGN)) continue;
+    bool same = (f & PF_IN_PREV) && ((pool.pmeta[g] & 0xFFFFu) == (pool.prev_meta[g] & 0xFFFFu));
+    if (same) {
+      const int32_t* a = pool.rows + D.rows_off + (g - D.part_off) * D.SLP;
+      const int32_t* b = pool.prev_rows + D.rows_off + (g - D.part_off) * D.SLP;
+      for (int i = 0; i < D.SLP; ++i) same &= (a[i] == b[i]);
+    }
+    if (!same) D.mismatch = 1;
+  }
+}
+
+// ---- plan.go:49-52: prevMap[p] = partitionsToAssign[p] = next[p] --------------------------------------
+__global__ void k_commit(DPool pool, long long n_parts_total) {
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n_parts_total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const DInst& D = pool.insts[pool.part_inst[g]];
+    const uint8_t f = pool.pflags[g];
+    if (!D.active || !D.mismatch || !(f & PF_IN_ASSIGN)) continue;
+    const int32_t* a = pool.rows + D.rows_off + (g - D.part_off) * D.SLP;
+    int32_t* b = pool.prev_rows + D.rows_off + (g - D.part_off) * D.SLP;
+    for (int i = 0; i < D.SLP; ++i) b[i] = a[i];
+    pool.prev_meta[g] = pool.pmeta[g] & 0xFFFFu;
+    pool.pflags[g] = f | PF_IN_PREV;
+  }
+}
+
+// ---- loop control of plan.go:32-56, one thread per instance --------------------------------------------
+__global__ void k_next_iter(DPool pool, int n_inst, int* any_active) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_inst) return;
+  DInst& D = pool.insts[i];
+  if (!D.active) return;
+  D.iters_run += 1;
+  if (!D.mismatch) { D.converged = 1; D.active = 0; return; }
+  D.converged = 0;
+  if (D.iters_run >= D.max_iters) { D.active = 0; return; }
+  D.mismatch = 0;
+  D.rm_active = 0;           // nodesToRemove = []string{}
+  D.add_active = 0;          // nodesToAdd = []string{} (non-nil: everyone lands in bucket "1")
+  D.add_is_nil = 0;
+  D.use_rest = 1;
+  D.P = D.PU;                // len(prevMap) after plan.go:49-52
+  atomicAdd(any_active, 1);
+}
+
+// ---- CalcPartitionMoves (moves.go:41-136), one thread per partition ------------------------------------------
+__global__ void k_calc_moves(int32_t n_parts, int32_t n_states, int32_t n_visit, const int32_t* __restrict__ slot_off,
+                             const int32_t* __restrict__ beg_rows, const int32_t* __restrict__ end_rows,
+                             int32_t favor_min, int32_t max_ops, int32_t* __restrict__ op_node,
+                             uint8_t* __restrict__ op_state, uint8_t* __restrict__ op_kind,
+                             int32_t* __restrict__ op_count) {
+  const int SL = slot_off[n_states];
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n_parts;
+       p += (long long)gridDim.x * blockDim.x) {
+    const int32_t* beg = beg_rows + p * SL;
+    const int32_t* end = end_rows + p * SL;
+    int32_t* on = op_node + p * max_ops;
+    uint8_t* os = op_state + p * max_ops;
+    uint8_t* ok = op_kind + p * max_ops;
+    int cnt = 0;
+    auto in_row = [&](const int32_t* row, int32_t node) { bool r = false; for (int i = 0; i < SL; ++i) r |= (row[i] == node); return r; };
+    auto emit = [&](int32_t node, int st, int kind) {                 // addMoves + seen, moves.go:51-58
+      for (int j = 0; j < cnt; ++j) if (on[j] == node) return;
+      if (cnt < max_ops) { on[cnt] = node; os[cnt] = (uint8_t)st; ok[cnt] = (uint8_t)kind; ++cnt; }
+    };
+    for (int step = 0; step < n_visit; ++step) {
+      const int si = favor_min ? n_visit - 1 - step : step;
+      const int lo = slot_off[si], hi = slot_off[si + 1];
+      for (int phase = 0; phase < 4; ++phase) {
+        // !favorMinNodes: promote, demote, add, del (moves.go:66-90); favorMinNodes: del, demote, promote, add (:92-116)
+        const int what = favor_min ? (phase == 0 ? 3 : phase == 1 ? 1 : phase == 2 ? 0 : 2) : phase;
+        if (what <= 1) {                      // findStateChanges, moves.go:121-136
+          const int jlo = what == 0 ? si + 1 : 0, jhi = what == 0 ? n_visit : si;
+          for (int i = lo; i < hi && end[i] != BLANCE_NO_NODE; ++i)
+            for (int j = jlo; j < jhi; ++j)
+              for (int b = slot_off[j]; b < slot_off[j + 1] && beg[b] != BLANCE_NO_NODE; ++b)
+                if (beg[b] == end[i]) emit(end[i], si, what == 0 ? BLANCE_OP_PROMOTE : BLANCE_OP_DEMOTE);
+        } else if (what == 2) {               // end[s] \ beg[s], restricted to adds = endAll \ begAll
+          for (int i = lo; i < hi && end[i] != BLANCE_NO_NODE; ++i)
+            if (!in_row(beg, end[i])) emit(end[i], si, BLANCE_OP_ADD);
+        } else {                              // beg[s] \ end[s], restricted to dels = begAll \ endAll
+          for (int i = lo; i < hi && beg[i] != BLANCE_NO_NODE; ++i)
+            if (!in_row(end, beg[i])) emit(beg[i], BLANCE_OP_STATE_NONE, BLANCE_OP_DEL);
+        }
+      }
+    }
+    op_count[p] = cnt;
+  }
+}
+
+}  // namespace blance_dev

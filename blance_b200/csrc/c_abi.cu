@@ -1,0 +1,629 @@
+// blance_b200/csrc/c_abi.cu — the C ABI of libblance_b200.so (include/blance_b200.h):
+// validation, pooling of a batch of plan instances into one set of device arrays,
+// the host side of the convergence loop (plan.go:32-56) and the launches.
+// No CPU fallback: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_segmented_radix_sort.cuh>
+
+#include "assign_pass.cuh"
+#include "aux_kernels.cuh"
+#include "blance_b200.h"
+#include "device_types.cuh"
+
+using namespace blance_dev;
+
+static std::string g_create_error;
+
+struct blance_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  std::mutex mu;
+  void* cub_tmp = nullptr;
+  size_t cub_tmp_bytes = 0;
+  std::vector<cudaEvent_t> events;   // pool for pass timing
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  int* d_any_active = nullptr;
+  int* h_any_active = nullptr;       // pinned
+};
+
+#define CK(call)                                                                           \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess) {                                                               \
+      char b_[512];                                                                        \
+      std::snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      ctx->err = b_;                                                                       \
+      return BLANCE_ERR_CUDA;                                                              \
+    }                                                                                      \
+  } while (0)
+
+static int fail(blance_ctx* ctx, int st, const std::string& msg) {
+  if (ctx) ctx->err = msg; else g_create_error = msg;
+  return st;
+}
+
+extern "C" int blance_version(void) { return 100; }
+
+extern "C" const char* blance_last_error(const blance_ctx* ctx) {
+  return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" int blance_ctx_create(blance_ctx** out, int device_id) {
+  if (!out) return fail(nullptr, BLANCE_ERR_INVALID_ARG, "blance_ctx_create: out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0)
+    return fail(nullptr, BLANCE_ERR_CUDA, std::string("no CUDA device available (") +
+                                              (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                              "); libblance_b200 has no CPU fallback");
+  if (device_id < 0) {
+    if (cudaGetDevice(&device_id) != cudaSuccess) device_id = 0;
+  }
+  if (device_id >= count) return fail(nullptr, BLANCE_ERR_INVALID_ARG, "blance_ctx_create: device id out of range");
+  blance_ctx* ctx = new blance_ctx();
+  ctx->device = device_id;
+  auto bail = [&](const char* what, cudaError_t er) {
+    std::string msg = std::string(what) + ": " + cudaGetErrorString(er);
+    delete ctx;
+    return fail(nullptr, BLANCE_ERR_CUDA, msg);
+  };
+  if ((e = cudaSetDevice(device_id)) != cudaSuccess) return bail("cudaSetDevice", e);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device_id)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+  ctx->sm_count = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  for (auto& ev : ctx->ev)
+    if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if ((e = cudaMalloc(&ctx->d_any_active, sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMallocHost(&ctx->h_any_active, sizeof(int))) != cudaSuccess) return bail("cudaMallocHost", e);
+  *out = ctx;
+  return BLANCE_OK;
+}
+
+extern "C" void blance_ctx_destroy(blance_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (auto ev : ctx->events) cudaEventDestroy(ev);
+  for (auto ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  if (ctx->cub_tmp) cudaFree(ctx->cub_tmp);
+  if (ctx->d_any_active) cudaFree(ctx->d_any_active);
+  if (ctx->h_any_active) cudaFreeHost(ctx->h_any_active);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+// ---------------------------------------------------------------------------------------
+// A batch of instances resident on the device.
+
+struct blance_plan {
+  int n_inst = 0;
+  std::vector<DInst> h_insts;          // initial descriptors (dynamic fields at their start values)
+  std::vector<long long> raw_rows_off, raw_shape_off;   // caller-layout offsets per instance
+  long long PT = 0, RT = 0, NT = 0, NUT = 0, CT = 0, N2T = 0, MT = 0, RRT = 0, RST = 0;
+  int max_N = 0, max_S = 0;
+  bool any_state_active[BL_S_MAX] = {};
+  void* arena = nullptr;               // one device allocation, carved below
+  size_t arena_bytes = 0;
+  DPool pool{};
+  // immutable copies of the mutable state, to replay the plan (blance_plan_run)
+  int32_t *rows_init = nullptr, *prev_rows_init = nullptr;
+  uint32_t *pmeta_init = nullptr, *prev_meta_init = nullptr;
+  uint8_t* pflags_init = nullptr;
+  // device staging in caller layout
+  int32_t *raw_a = nullptr, *raw_b = nullptr;           // cur/prev rows in, next rows out (raw_a)
+  uint8_t *rawsh_a = nullptr, *rawsh_b = nullptr;       // cur/prev shape in, next shape (a) / warn (b) out
+  long long *d_raw_rows_off = nullptr, *d_raw_shape_off = nullptr;
+  int* d_seg_off = nullptr;            // [n_inst+1] partition offsets for the segmented sort
+  // pinned host staging (batch concatenation and results)
+  void* h_stage = nullptr;
+  size_t h_stage_bytes = 0;
+  float last_kernel_ms = 0, last_pass_ms = 0;
+  int pass_launches = 0;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int validate(blance_ctx* ctx, const blance_plan_in* in, int idx) {
+  char b[256];
+  auto bad = [&](const char* what, int st = BLANCE_ERR_INVALID_ARG) {
+    std::snprintf(b, sizeof b, "instance %d: %s", idx, what);
+    return fail(ctx, st, b);
+  };
+  if (!in) return bad("plan_in is NULL");
+  if (in->n_nodes < 0 || in->n_node_ids < in->n_nodes || in->n_states < 0 || in->n_parts < 0 || in->n_slots < 0)
+    return bad("negative size or n_node_ids < n_nodes");
+  if (in->n_states > BL_S_MAX) return bad("more than 8 model states", BLANCE_ERR_UNSUPPORTED);
+  if (in->n_slots > BL_SLP_MAX) return bad("more than 32 slots per row", BLANCE_ERR_UNSUPPORTED);
+  if (in->n_nodes > 8192) return bad("more than 8192 nodes", BLANCE_ERR_UNSUPPORTED);
+  if (in->n_states > 0 && (!in->state_priority || !in->state_constraints || !in->state_slot_off ||
+                           !in->state_stickiness || !in->state_has_stickiness))
+    return bad("state tables are NULL");
+  if (in->n_states > 0 && (in->top_state < 0 || in->top_state >= in->n_states)) return bad("top_state out of range");
+  if (in->n_states > 0 && in->state_slot_off[in->n_states] != in->n_slots) return bad("state_slot_off[S] != n_slots");
+  for (int s = 0; s < in->n_states; ++s) {
+    if (in->state_slot_off[s + 1] < in->state_slot_off[s]) return bad("state_slot_off not monotone");
+    if (in->state_constraints[s] > BL_K_MAX) return bad("constraints > 16", BLANCE_ERR_UNSUPPORTED);
+    if (in->state_constraints[s] > in->state_slot_off[s + 1] - in->state_slot_off[s])
+      return bad("a state's slot range is smaller than its constraints");
+  }
+  if (in->n_parts > 0 && (!in->part_in_prev || !in->part_in_assign || !in->part_weight || !in->part_has_weight ||
+                          !in->part_name_rank || !in->prev_shape || !in->cur_shape))
+    return bad("partition tables are NULL");
+  if (in->n_parts > 0 && in->n_slots > 0 && (!in->prev_rows || !in->cur_rows)) return bad("row tables are NULL");
+  if (in->n_node_ids > 0 && (!in->node_removed || !in->node_added)) return bad("node flag tables are NULL");
+  if (in->n_nodes > 0 && in->has_node_weights && (!in->node_weight || !in->node_has_weight)) return bad("node weight tables are NULL");
+  if (in->n_parts >= (1 << 30)) return bad("2^30 or more partitions", BLANCE_ERR_UNSUPPORTED);
+  if (in->has_hier_rules) {
+    if (!in->rule_off) return bad("rule_off is NULL");
+    if (in->n_rules > 0 && !in->ie_mask) return bad("ie_mask is NULL");
+    if (in->n_hier_bits < in->n_nodes) return bad("n_hier_bits < n_nodes");
+    if ((in->n_hier_bits + 31) / 32 > 128) return bad("hierarchy universe above 4096 bits", BLANCE_ERR_UNSUPPORTED);
+    for (int s = 0; s < in->n_states; ++s)
+      if ((in->rule_off[s + 1] - in->rule_off[s]) * std::max(0, in->state_constraints[s]) > BL_PICK_MAX)
+        return bad("rules x constraints > 32 for one state", BLANCE_ERR_UNSUPPORTED);
+  }
+  if (in->booster_kind != BLANCE_BOOSTER_NONE && in->booster_kind != BLANCE_BOOSTER_CBGT_MAX)
+    return bad("unknown booster_kind", BLANCE_ERR_UNSUPPORTED);
+  return BLANCE_OK;
+}
+
+static void plan_release(blance_plan* pl) {
+  if (!pl) return;
+  if (pl->arena) cudaFree(pl->arena);
+  if (pl->h_stage) cudaFreeHost(pl->h_stage);
+  delete pl;
+}
+
+static int grid_for(const blance_ctx* ctx, long long n, int block) {
+  long long want = (n + block - 1) / block;
+  long long cap = (long long)ctx->sm_count * 8;      // multiples of the SM count; kernels are grid-stride
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+static int upload(blance_ctx* ctx, int n, const blance_plan_in* ins, blance_plan** out_plan) {
+  *out_plan = nullptr;
+  if (n <= 0) return fail(ctx, BLANCE_ERR_INVALID_ARG, "batch size must be positive");
+  for (int i = 0; i < n; ++i) {
+    int st = validate(ctx, &ins[i], i);
+    if (st != BLANCE_OK) return st;
+  }
+  CK(cudaSetDevice(ctx->device));
+  blance_plan* pl = new blance_plan();
+  pl->n_inst = n;
+  pl->h_insts.resize(n);
+  pl->raw_rows_off.resize(n + 1);
+  pl->raw_shape_off.resize(n + 1);
+  std::vector<int> seg_off(n + 1);
+  for (int i = 0; i < n; ++i) {
+    const blance_plan_in& in = ins[i];
+    DInst& D = pl->h_insts[i];
+    std::memset(&D, 0, sizeof D);
+    D.N = in.n_nodes; D.NU = in.n_node_ids; D.S = in.n_states; D.PU = in.n_parts; D.SL = in.n_slots;
+    D.SLP = std::max(4, (int)align_up((size_t)in.n_slots, 4));
+    D.HW = in.has_hier_rules ? (in.n_hier_bits + 31) / 32 : 0;
+    D.n_rules = in.has_hier_rules ? in.n_rules : 0;
+    D.top_state = in.top_state; D.booster = in.booster_kind;
+    D.has_part_weights = in.has_part_weights; D.has_node_weights = in.has_node_weights;
+    D.has_hier_rules = in.has_hier_rules; D.max_iters = in.max_iters;
+    for (int s = 0; s < in.n_states; ++s) {
+      D.state_priority[s] = in.state_priority[s];
+      D.state_constraints[s] = in.state_constraints[s];
+      D.state_slot_off[s] = in.state_slot_off[s];
+      D.state_stickiness[s] = in.state_stickiness[s];
+      D.state_has_stickiness[s] = in.state_has_stickiness[s];
+      D.rule_off[s] = in.has_hier_rules ? in.rule_off[s] : 0;
+      if (in.state_constraints[s] > 0) pl->any_state_active[s] = true;
+    }
+    D.state_slot_off[in.n_states] = in.n_slots;
+    D.rule_off[in.n_states] = in.has_hier_rules ? in.rule_off[in.n_states] : 0;
+    int n_prev = 0, n_assign = 0, n_valid = 0, rm_active = 0;
+    for (int p = 0; p < in.n_parts; ++p) { n_prev += in.part_in_prev[p] != 0; n_assign += in.part_in_assign[p] != 0; }
+    for (int q = 0; q < in.n_nodes; ++q) n_valid += in.node_removed[q] == 0;
+    for (int q = 0; q < in.n_node_ids; ++q) rm_active |= in.node_removed[q] != 0;
+    D.n_assign = n_assign; D.n_valid = n_valid;
+    D.P = n_prev; D.rm_active = rm_active; D.add_active = 1; D.add_is_nil = in.add_is_nil; D.use_rest = 0;
+    D.active = in.max_iters > 0 ? 1 : 0;
+    D.part_off = pl->PT; D.rows_off = pl->RT; D.node_off = pl->NT; D.nodeid_off = pl->NUT;
+    D.counts_off = pl->CT; D.n2n_off = pl->N2T; D.mask_off = pl->MT;
+    pl->raw_rows_off[i] = pl->RRT; pl->raw_shape_off[i] = pl->RST;
+    seg_off[i] = (int)pl->PT;
+    pl->PT += D.PU; pl->RT += (long long)D.PU * D.SLP; pl->NT += D.N; pl->NUT += D.NU;
+    pl->CT += (long long)D.S * D.N; pl->N2T += (long long)(D.NU + 1) * D.N;
+    pl->MT += (long long)D.n_rules * (D.NU + 1) * D.HW;
+    pl->RRT += (long long)D.PU * D.SL; pl->RST += (long long)D.PU * D.S;
+    pl->max_N = std::max(pl->max_N, D.N); pl->max_S = std::max(pl->max_S, D.S);
+  }
+  seg_off[n] = (int)pl->PT;
+  pl->raw_rows_off[n] = pl->RRT; pl->raw_shape_off[n] = pl->RST;
+  if (pl->PT >= (1LL << 31)) { plan_release(pl); return fail(ctx, BLANCE_ERR_UNSUPPORTED, "2^31 or more partitions in one batch"); }
+
+  // ---- carve one device arena ------------------------------------------------------------
+  struct Slice { void** ptr; size_t bytes; };
+  std::vector<Slice> slices;
+  DPool& P = pl->pool;
+  const size_t PT = (size_t)pl->PT + 1, RT = (size_t)pl->RT + 4, NT = (size_t)pl->NT + 1, NUT = (size_t)pl->NUT + 1;
+  const size_t CT = (size_t)pl->CT + 1, N2T = (size_t)pl->N2T + 1, MT = (size_t)pl->MT + 1;
+  const size_t RRT = (size_t)pl->RRT + 1, RST = (size_t)pl->RST + 1;
+  const int32_t *c_pweight, *c_rank, *c_inst, *c_nw, *c_ef, *c_er;
+  const uint8_t *c_rm, *c_ad, *c_hw;
+  const uint32_t* c_mask;
+#define SL_(p, T, cnt) slices.push_back(Slice{(void**)&(p), sizeof(T) * (cnt)})
+  SL_(P.rows, int32_t, RT); SL_(P.prev_rows, int32_t, RT); SL_(pl->rows_init, int32_t, RT); SL_(pl->prev_rows_init, int32_t, RT);
+  SL_(P.pmeta, uint32_t, PT); SL_(P.prev_meta, uint32_t, PT); SL_(pl->pmeta_init, uint32_t, PT); SL_(pl->prev_meta_init, uint32_t, PT);
+  SL_(P.pflags, uint8_t, PT); SL_(pl->pflags_init, uint8_t, PT);
+  SL_(c_pweight, int32_t, PT); SL_(c_rank, int32_t, PT); SL_(c_inst, int32_t, PT);
+  SL_(P.keys, unsigned long long, PT); SL_(P.keys_alt, unsigned long long, PT); SL_(P.order, int32_t, PT); SL_(P.order_alt, int32_t, PT);
+  SL_(c_rm, uint8_t, NUT); SL_(c_ad, uint8_t, NUT); SL_(c_nw, int32_t, NT); SL_(c_hw, uint8_t, NT);
+  SL_(c_ef, int32_t, NT); SL_(c_er, int32_t, NT);
+  SL_(P.counts, int32_t, CT); SL_(P.n2n, int32_t, N2T); SL_(c_mask, uint32_t, MT);
+  SL_(P.insts, DInst, (size_t)n);
+  SL_(pl->raw_a, int32_t, RRT); SL_(pl->raw_b, int32_t, RRT); SL_(pl->rawsh_a, uint8_t, RST); SL_(pl->rawsh_b, uint8_t, RST);
+  SL_(pl->d_raw_rows_off, long long, (size_t)n + 1); SL_(pl->d_raw_shape_off, long long, (size_t)n + 1);
+  SL_(pl->d_seg_off, int, (size_t)n + 1);
+#undef SL_
+  size_t total = 0;
+  for (auto& s : slices) total += align_up(s.bytes, 256);
+  cudaError_t e = cudaMalloc(&pl->arena, total);
+  if (e != cudaSuccess) {
+    plan_release(pl);
+    return fail(ctx, BLANCE_ERR_NOMEM, std::string("cudaMalloc of the plan arena failed: ") + cudaGetErrorString(e));
+  }
+  pl->arena_bytes = total;
+  {
+    size_t off = 0;
+    for (auto& s : slices) { *s.ptr = (char*)pl->arena + off; off += align_up(s.bytes, 256); }
+  }
+  P.pweight = c_pweight; P.name_rank = c_rank; P.part_inst = c_inst;
+  P.node_removed = c_rm; P.node_added = c_ad; P.node_weight = c_nw; P.node_has_weight = c_hw;
+  P.extra_first = c_ef; P.extra_rest = c_er; P.ie_mask = c_mask;
+
+  // ---- pinned staging: concatenate the batch in caller layout, then copy ------------------
+  const size_t stage_bytes = align_up(sizeof(int32_t) * RRT, 256) * 2 + align_up(RST, 256) * 2 + align_up(PT, 256) +
+                             align_up(sizeof(int32_t) * PT, 256) * 3 + align_up(NUT, 256) * 2 +
+                             align_up(sizeof(int32_t) * NT, 256) * 3 + align_up(NT, 256) + align_up(sizeof(uint32_t) * MT, 256);
+  e = cudaMallocHost(&pl->h_stage, stage_bytes);
+  if (e != cudaSuccess) {
+    plan_release(pl);
+    return fail(ctx, BLANCE_ERR_NOMEM, std::string("cudaMallocHost of the staging buffer failed: ") + cudaGetErrorString(e));
+  }
+  pl->h_stage_bytes = stage_bytes;
+  char* hp = (char*)pl->h_stage;
+  auto carve = [&](size_t bytes) { char* r = hp; hp += align_up(bytes, 256); return r; };
+  int32_t* h_cur = (int32_t*)carve(sizeof(int32_t) * RRT);
+  int32_t* h_prev = (int32_t*)carve(sizeof(int32_t) * RRT);
+  uint8_t* h_csh = (uint8_t*)carve(RST);
+  uint8_t* h_psh = (uint8_t*)carve(RST);
+  uint8_t* h_flags = (uint8_t*)carve(PT);
+  int32_t* h_pw = (int32_t*)carve(sizeof(int32_t) * PT);
+  int32_t* h_rank = (int32_t*)carve(sizeof(int32_t) * PT);
+  int32_t* h_inst = (int32_t*)carve(sizeof(int32_t) * PT);
+  uint8_t* h_rm = (uint8_t*)carve(NUT);
+  uint8_t* h_ad = (uint8_t*)carve(NUT);
+  int32_t* h_nw = (int32_t*)carve(sizeof(int32_t) * NT);
+  int32_t* h_ef = (int32_t*)carve(sizeof(int32_t) * NT);
+  int32_t* h_er = (int32_t*)carve(sizeof(int32_t) * NT);
+  uint8_t* h_hw = (uint8_t*)carve(NT);
+  uint32_t* h_mask = (uint32_t*)carve(sizeof(uint32_t) * MT);
+  for (int i = 0; i < n; ++i) {
+    const blance_plan_in& in = ins[i];
+    const DInst& D = pl->h_insts[i];
+    const size_t rr = (size_t)D.PU * D.SL, rs = (size_t)D.PU * D.S;
+    if (rr) { std::memcpy(h_cur + pl->raw_rows_off[i], in.cur_rows, sizeof(int32_t) * rr);
+              std::memcpy(h_prev + pl->raw_rows_off[i], in.prev_rows, sizeof(int32_t) * rr); }
+    if (rs) { std::memcpy(h_csh + pl->raw_shape_off[i], in.cur_shape, rs); std::memcpy(h_psh + pl->raw_shape_off[i], in.prev_shape, rs); }
+    for (int p = 0; p < D.PU; ++p) {
+      const size_t g = (size_t)D.part_off + p;
+      h_flags[g] = (uint8_t)((in.part_in_prev[p] ? PF_IN_PREV : 0) | (in.part_in_assign[p] ? PF_IN_ASSIGN : 0) |
+                             (in.part_has_weight[p] ? PF_HAS_WEIGHT : 0));
+      h_pw[g] = in.part_weight[p];
+      h_rank[g] = in.part_name_rank[p];
+      h_inst[g] = i;
+    }
+    if (D.NU) { std::memcpy(h_rm + D.nodeid_off, in.node_removed, D.NU); std::memcpy(h_ad + D.nodeid_off, in.node_added, D.NU); }
+    for (int q = 0; q < D.N; ++q) {
+      h_nw[D.node_off + q] = in.has_node_weights ? in.node_weight[q] : 0;
+      h_hw[D.node_off + q] = in.has_node_weights ? in.node_has_weight[q] : 0;
+      h_ef[D.node_off + q] = in.extra_tot_first ? in.extra_tot_first[q] : 0;
+      h_er[D.node_off + q] = in.extra_tot_rest ? in.extra_tot_rest[q] : 0;
+    }
+    const size_t mw = (size_t)D.n_rules * (D.NU + 1) * D.HW;
+    if (mw) std::memcpy(h_mask + D.mask_off, in.ie_mask, sizeof(uint32_t) * mw);
+  }
+  cudaStream_t st = ctx->stream;
+#define H2D(dst, src, bytes) do { if ((bytes) > 0) { e = cudaMemcpyAsync((void*)(dst), (src), (bytes), cudaMemcpyHostToDevice, st); \
+    if (e != cudaSuccess) { plan_release(pl); return fail(ctx, BLANCE_ERR_CUDA, std::string("H2D copy failed: ") + cudaGetErrorString(e)); } } } while (0)
+  H2D(pl->raw_a, h_cur, sizeof(int32_t) * (size_t)pl->RRT); H2D(pl->raw_b, h_prev, sizeof(int32_t) * (size_t)pl->RRT);
+  H2D(pl->rawsh_a, h_csh, (size_t)pl->RST); H2D(pl->rawsh_b, h_psh, (size_t)pl->RST);
+  H2D(pl->pflags_init, h_flags, (size_t)pl->PT); H2D(c_pweight, h_pw, sizeof(int32_t) * (size_t)pl->PT);
+  H2D(c_rank, h_rank, sizeof(int32_t) * (size_t)pl->PT); H2D(c_inst, h_inst, sizeof(int32_t) * (size_t)pl->PT);
+  H2D(c_rm, h_rm, (size_t)pl->NUT); H2D(c_ad, h_ad, (size_t)pl->NUT);
+  H2D(c_nw, h_nw, sizeof(int32_t) * (size_t)pl->NT); H2D(c_hw, h_hw, (size_t)pl->NT);
+  H2D(c_ef, h_ef, sizeof(int32_t) * (size_t)pl->NT); H2D(c_er, h_er, sizeof(int32_t) * (size_t)pl->NT);
+  H2D(c_mask, h_mask, sizeof(uint32_t) * (size_t)pl->MT);
+  H2D(P.insts, pl->h_insts.data(), sizeof(DInst) * (size_t)n);
+  H2D(pl->d_raw_rows_off, pl->raw_rows_off.data(), sizeof(long long) * (size_t)(n + 1));
+  H2D(pl->d_raw_shape_off, pl->raw_shape_off.data(), sizeof(long long) * (size_t)(n + 1));
+  H2D(pl->d_seg_off, seg_off.data(), sizeof(int) * (size_t)(n + 1));
+#undef H2D
+  // device layout of the rows / shapes, into the *_init copies via the working arrays
+  if (pl->PT > 0) {
+    k_unpack<<<grid_for(ctx, pl->PT, 256), 256, 0, st>>>(P, pl->raw_a, pl->raw_b, pl->rawsh_a, pl->rawsh_b,
+                                                        pl->d_raw_rows_off, pl->d_raw_shape_off, pl->PT);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(pl->rows_init, P.rows, sizeof(int32_t) * (size_t)pl->RT, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(pl->prev_rows_init, P.prev_rows, sizeof(int32_t) * (size_t)pl->RT, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(pl->pmeta_init, P.pmeta, sizeof(uint32_t) * (size_t)pl->PT, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(pl->prev_meta_init, P.prev_meta, sizeof(uint32_t) * (size_t)pl->PT, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) { plan_release(pl); return fail(ctx, BLANCE_ERR_CUDA, std::string("upload failed: ") + cudaGetErrorString(e)); }
+  }
+  // sort scratch
+  size_t need = 0, need2 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, need, P.keys_alt, P.keys, P.order_alt, P.order, (int)pl->PT, 0, 64, st);
+  cub::DeviceSegmentedRadixSort::SortPairs(nullptr, need2, P.keys_alt, P.keys, P.order_alt, P.order, (int)pl->PT, n,
+                                           pl->d_seg_off, pl->d_seg_off + 1, 0, 64, st);
+  need = std::max(need, need2);
+  if (need > ctx->cub_tmp_bytes) {
+    if (ctx->cub_tmp) cudaFree(ctx->cub_tmp);
+    ctx->cub_tmp = nullptr; ctx->cub_tmp_bytes = 0;
+    e = cudaMalloc(&ctx->cub_tmp, need);
+    if (e != cudaSuccess) { plan_release(pl); return fail(ctx, BLANCE_ERR_NOMEM, "cudaMalloc of the sort scratch failed"); }
+    ctx->cub_tmp_bytes = need;
+  }
+  e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { plan_release(pl); return fail(ctx, BLANCE_ERR_CUDA, std::string("upload failed: ") + cudaGetErrorString(e)); }
+  *out_plan = pl;
+  return BLANCE_OK;
+}
+
+static cudaEvent_t get_event(blance_ctx* ctx, size_t idx) {
+  while (ctx->events.size() <= idx) {
+    cudaEvent_t ev;
+    if (cudaEventCreate(&ev) != cudaSuccess) return nullptr;
+    ctx->events.push_back(ev);
+  }
+  return ctx->events[idx];
+}
+
+template <int NPT>
+static void launch_pass(const DPool& P, int n_inst, int T, int s, cudaStream_t st) {
+  k_assign_pass<NPT><<<n_inst, T, 0, st>>>(P, s);
+}
+
+static int run(blance_ctx* ctx, blance_plan* pl) {
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  DPool& P = pl->pool;
+  const int n = pl->n_inst;
+  // restore the mutable state
+  if (pl->PT > 0) {
+    CK(cudaMemcpyAsync(P.rows, pl->rows_init, sizeof(int32_t) * (size_t)pl->RT, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(P.prev_rows, pl->prev_rows_init, sizeof(int32_t) * (size_t)pl->RT, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(P.pmeta, pl->pmeta_init, sizeof(uint32_t) * (size_t)pl->PT, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(P.prev_meta, pl->prev_meta_init, sizeof(uint32_t) * (size_t)pl->PT, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(P.pflags, pl->pflags_init, (size_t)pl->PT, cudaMemcpyDeviceToDevice, st));
+  }
+  CK(cudaMemcpyAsync(P.insts, pl->h_insts.data(), sizeof(DInst) * (size_t)n, cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(ctx->ev[1], st));
+
+  int T = std::min(1024, (int)align_up((size_t)std::max(1, pl->max_N), 32));
+  int npt = (pl->max_N + T - 1) / T;
+  if (npt < 1) npt = 1;
+  int any_active = 0;
+  for (int i = 0; i < n; ++i) any_active += pl->h_insts[i].active;
+  const int blk = 256;
+  const int grid = grid_for(ctx, pl->PT, blk);
+  size_t n_ev = 0;
+  pl->pass_launches = 0;
+  const bool smem_hist = (n == 1) && ((size_t)pl->h_insts[0].S * pl->h_insts[0].N * sizeof(int32_t) <= 40 * 1024);
+  int guard = 0;
+  while (any_active > 0 && pl->PT > 0) {
+    if (++guard > 100000) return fail(ctx, BLANCE_ERR_CUDA, "convergence loop did not terminate");
+    k_prepare_rows<<<grid, blk, 0, st>>>(P, pl->PT);
+    CK(cudaMemsetAsync(P.counts, 0, sizeof(int32_t) * (size_t)(pl->CT + 1), st));
+    if (smem_hist)
+      k_count_prev<true><<<std::min(grid, ctx->sm_count * 2), blk, (size_t)pl->h_insts[0].S * pl->h_insts[0].N * sizeof(int32_t), st>>>(P, pl->PT);
+    else
+      k_count_prev<false><<<grid, blk, 0, st>>>(P, pl->PT);
+    for (int s = 0; s < pl->max_S; ++s) {
+      if (!pl->any_state_active[s]) continue;
+      k_build_keys<<<grid, blk, 0, st>>>(P, s, pl->PT);
+      size_t tmp = ctx->cub_tmp_bytes;
+      if (n == 1)
+        CK(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp, tmp, P.keys_alt, P.keys, P.order_alt, P.order, (int)pl->PT, 0, 64, st));
+      else
+        CK(cub::DeviceSegmentedRadixSort::SortPairs(ctx->cub_tmp, tmp, P.keys_alt, P.keys, P.order_alt, P.order, (int)pl->PT,
+                                                    n, pl->d_seg_off, pl->d_seg_off + 1, 0, 64, st));
+      CK(cudaMemsetAsync(P.n2n, 0, sizeof(int32_t) * (size_t)(pl->N2T + 1), st));     // plan.go:266
+      cudaEvent_t e0 = get_event(ctx, n_ev), e1 = get_event(ctx, n_ev + 1);
+      if (e0 && e1 && n_ev < 256) CK(cudaEventRecord(e0, st));
+      switch (npt) {
+        case 1: launch_pass<1>(P, n, T, s, st); break;
+        case 2: launch_pass<2>(P, n, T, s, st); break;
+        case 3: case 4: launch_pass<4>(P, n, T, s, st); break;
+        default: launch_pass<8>(P, n, T, s, st); break;
+      }
+      CK(cudaGetLastError());
+      if (e0 && e1 && n_ev < 256) { CK(cudaEventRecord(e1, st)); n_ev += 2; }
+      pl->pass_launches++;
+    }
+    k_compare<<<grid, blk, 0, st>>>(P, pl->PT);
+    k_commit<<<grid, blk, 0, st>>>(P, pl->PT);
+    CK(cudaMemsetAsync(ctx->d_any_active, 0, sizeof(int), st));
+    k_next_iter<<<(n + 127) / 128, 128, 0, st>>>(P, n, ctx->d_any_active);
+    CK(cudaMemcpyAsync(ctx->h_any_active, ctx->d_any_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    any_active = *ctx->h_any_active;
+  }
+  CK(cudaEventRecord(ctx->ev[2], st));
+  CK(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]));
+  pl->last_kernel_ms = ms;
+  float pass = 0.f;
+  for (size_t i = 0; i + 1 < n_ev; i += 2) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, ctx->events[i], ctx->events[i + 1]) == cudaSuccess) pass += t;
+  }
+  pl->last_pass_ms = pass;
+  return BLANCE_OK;
+}
+
+static int fetch(blance_ctx* ctx, blance_plan* pl, blance_plan_out* outs) {
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int n = pl->n_inst;
+  if (pl->PT > 0) {
+    k_pack<<<grid_for(ctx, pl->PT, 256), 256, 0, st>>>(pl->pool, pl->raw_a, pl->rawsh_a, pl->rawsh_b, pl->d_raw_rows_off,
+                                                      pl->d_raw_shape_off, pl->PT);
+    CK(cudaGetLastError());
+  }
+  // results land in the pinned staging buffer (its head is large enough: it held cur+prev rows)
+  char* hp = (char*)pl->h_stage;
+  int32_t* h_rows = (int32_t*)hp;
+  hp += align_up(sizeof(int32_t) * ((size_t)pl->RRT + 1), 256) * 2;
+  uint8_t* h_shape = (uint8_t*)hp;
+  hp += align_up((size_t)pl->RST + 1, 256);
+  uint8_t* h_warn = (uint8_t*)hp;
+  if (pl->RRT) CK(cudaMemcpyAsync(h_rows, pl->raw_a, sizeof(int32_t) * (size_t)pl->RRT, cudaMemcpyDeviceToHost, st));
+  if (pl->RST) {
+    CK(cudaMemcpyAsync(h_shape, pl->rawsh_a, (size_t)pl->RST, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_warn, pl->rawsh_b, (size_t)pl->RST, cudaMemcpyDeviceToHost, st));
+  }
+  std::vector<DInst> fin(n);
+  CK(cudaMemcpyAsync(fin.data(), pl->pool.insts, sizeof(DInst) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (int i = 0; i < n; ++i) {
+    const DInst& D = pl->h_insts[i];
+    blance_plan_out& o = outs[i];
+    const size_t rr = (size_t)D.PU * D.SL, rs = (size_t)D.PU * D.S;
+    if (rr && o.next_rows) std::memcpy(o.next_rows, h_rows + pl->raw_rows_off[i], sizeof(int32_t) * rr);
+    if (rs && o.next_shape) std::memcpy(o.next_shape, h_shape + pl->raw_shape_off[i], rs);
+    if (rs && o.warn) std::memcpy(o.warn, h_warn + pl->raw_shape_off[i], rs);
+    o.iters_run = fin[i].iters_run;
+    o.converged = fin[i].converged;
+    o.steps = fin[i].steps;
+    o.kernel_ms = pl->last_kernel_ms;
+    o.pass_ms = pl->last_pass_ms;
+    o.device_ms = 0.f;
+  }
+  return BLANCE_OK;
+}
+
+extern "C" int blance_plan_upload(blance_ctx* ctx, const blance_plan_in* in, blance_plan** plan) {
+  if (!ctx) return fail(nullptr, BLANCE_ERR_INVALID_ARG, "ctx is NULL");
+  if (!plan) return fail(ctx, BLANCE_ERR_INVALID_ARG, "plan is NULL");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  return upload(ctx, 1, in, plan);
+}
+
+extern "C" int blance_plan_run(blance_ctx* ctx, blance_plan* plan) {
+  if (!ctx || !plan) return fail(ctx, BLANCE_ERR_INVALID_ARG, "ctx or plan is NULL");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  return run(ctx, plan);
+}
+
+extern "C" int blance_plan_fetch(blance_ctx* ctx, blance_plan* plan, blance_plan_out* out) {
+  if (!ctx || !plan || !out) return fail(ctx, BLANCE_ERR_INVALID_ARG, "ctx, plan or out is NULL");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  return fetch(ctx, plan, out);
+}
+
+extern "C" void blance_plan_free(blance_ctx* ctx, blance_plan* plan) {
+  if (!plan) return;
+  if (ctx) { std::lock_guard<std::mutex> g(ctx->mu); cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); plan_release(plan); }
+  else plan_release(plan);
+}
+
+static int plan_batch(blance_ctx* ctx, int32_t n, const blance_plan_in* in, blance_plan_out* out) {
+  if (!ctx) return fail(nullptr, BLANCE_ERR_INVALID_ARG, "ctx is NULL");
+  if (!in || !out) return fail(ctx, BLANCE_ERR_INVALID_ARG, "in or out is NULL");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  blance_plan* pl = nullptr;
+  int st = upload(ctx, n, in, &pl);
+  if (st != BLANCE_OK) return st;
+  st = run(ctx, pl);
+  if (st == BLANCE_OK) st = fetch(ctx, pl, out);
+  if (st == BLANCE_OK) {
+    cudaEventRecord(ctx->ev[3], ctx->stream);
+    cudaEventSynchronize(ctx->ev[3]);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]);
+    for (int i = 0; i < n; ++i) out[i].device_ms = ms;
+  }
+  plan_release(pl);
+  return st;
+}
+
+extern "C" int blance_plan_next_map(blance_ctx* ctx, const blance_plan_in* in, blance_plan_out* out) {
+  return plan_batch(ctx, 1, in, out);
+}
+
+extern "C" int blance_plan_next_map_batch(blance_ctx* ctx, int32_t n, const blance_plan_in* in, blance_plan_out* out) {
+  return plan_batch(ctx, n, in, out);
+}
+
+extern "C" int blance_calc_partition_moves(blance_ctx* ctx, int32_t n_parts, int32_t n_states, int32_t n_visit_states,
+                                           const int32_t* state_slot_off, const int32_t* beg_rows,
+                                           const int32_t* end_rows, int32_t favor_min_nodes, int32_t max_ops,
+                                           int32_t* op_node, uint8_t* op_state, uint8_t* op_kind, int32_t* op_count) {
+  if (!ctx) return fail(nullptr, BLANCE_ERR_INVALID_ARG, "ctx is NULL");
+  if (n_parts < 0 || n_states < 0 || n_visit_states < 0 || n_visit_states > n_states || !state_slot_off || max_ops < 0)
+    return fail(ctx, BLANCE_ERR_INVALID_ARG, "blance_calc_partition_moves: bad sizes");
+  if (n_parts == 0) return BLANCE_OK;
+  const int SL = state_slot_off[n_states];
+  if (SL > 0 && (!beg_rows || !end_rows)) return fail(ctx, BLANCE_ERR_INVALID_ARG, "rows are NULL");
+  if (!op_node || !op_state || !op_kind || !op_count) return fail(ctx, BLANCE_ERR_INVALID_ARG, "outputs are NULL");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t rows_b = sizeof(int32_t) * (size_t)n_parts * std::max(SL, 1), ops = (size_t)n_parts * std::max(max_ops, 1);
+  char* d = nullptr;
+  const size_t o_slot = 0, o_beg = align_up(sizeof(int32_t) * (n_states + 1), 256), o_end = o_beg + align_up(rows_b, 256),
+               o_node = o_end + align_up(rows_b, 256), o_state = o_node + align_up(sizeof(int32_t) * ops, 256),
+               o_kind = o_state + align_up(ops, 256), o_cnt = o_kind + align_up(ops, 256),
+               total = o_cnt + align_up(sizeof(int32_t) * (size_t)n_parts, 256);
+  CK(cudaMalloc((void**)&d, total));
+  int rc = BLANCE_OK;
+  auto step = [&](cudaError_t e, const char* what) {
+    if (e != cudaSuccess && rc == BLANCE_OK) rc = fail(ctx, BLANCE_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  };
+  step(cudaMemcpyAsync(d + o_slot, state_slot_off, sizeof(int32_t) * (n_states + 1), cudaMemcpyHostToDevice, st), "H2D");
+  if (SL > 0) {
+    step(cudaMemcpyAsync(d + o_beg, beg_rows, sizeof(int32_t) * (size_t)n_parts * SL, cudaMemcpyHostToDevice, st), "H2D");
+    step(cudaMemcpyAsync(d + o_end, end_rows, sizeof(int32_t) * (size_t)n_parts * SL, cudaMemcpyHostToDevice, st), "H2D");
+  }
+  if (rc == BLANCE_OK) {
+    k_calc_moves<<<grid_for(ctx, n_parts, 128), 128, 0, st>>>(n_parts, n_states, n_visit_states, (const int32_t*)(d + o_slot),
+                                                             (const int32_t*)(d + o_beg), (const int32_t*)(d + o_end),
+                                                             favor_min_nodes, max_ops, (int32_t*)(d + o_node),
+                                                             (uint8_t*)(d + o_state), (uint8_t*)(d + o_kind), (int32_t*)(d + o_cnt));
+    step(cudaGetLastError(), "k_calc_moves");
+  }
+  if (max_ops > 0) {
+    step(cudaMemcpyAsync(op_node, d + o_node, sizeof(int32_t) * (size_t)n_parts * max_ops, cudaMemcpyDeviceToHost, st), "D2H");
+    step(cudaMemcpyAsync(op_state, d + o_state, (size_t)n_parts * max_ops, cudaMemcpyDeviceToHost, st), "D2H");
+    step(cudaMemcpyAsync(op_kind, d + o_kind, (size_t)n_parts * max_ops, cudaMemcpyDeviceToHost, st), "D2H");
+  }
+  step(cudaMemcpyAsync(op_count, d + o_cnt, sizeof(int32_t) * (size_t)n_parts, cudaMemcpyDeviceToHost, st), "D2H");
+  step(cudaStreamSynchronize(st), "sync");
+  cudaFree(d);
+  return rc;
+}

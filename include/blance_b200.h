@@ -1,0 +1,185 @@
+/* include/blance_b200.h — C ABI of libblance_b200.so (B200 / sm_100a).
+ *
+ * This is the drop-in boundary for blance's planner hot path.  The reference
+ * (couchbase/blance, pure Go) has no FFI of its own: its boundary is the
+ * exported Go API.  A Go host keeps api.go's types and replaces the BODY of
+ *
+ *     PlanNextMapEx       api.go:147-157  -> planNextMapEx      plan.go:23-58
+ *     CalcPartitionMoves  moves.go:41-119
+ *
+ * with a cgo call into the two entry points below (INTEGRATION.md shows the
+ * binding).  Strings never cross: the host interns node / state / partition
+ * names to dense int32 ids and passes flat, caller-owned arrays.  All pointers
+ * are HOST pointers unless an entry point says otherwise; nothing is retained
+ * after a call returns.  Every call returns 0 on success or a negative
+ * blance_status; blance_last_error() describes the failure.  There is no CPU
+ * fallback: without a usable CUDA device every compute entry point fails.
+ *
+ * Id spaces
+ *   node id      0 .. n_nodes-1 = position in nodesAll (nodePositions, plan.go:72-75);
+ *                n_nodes .. n_node_ids-1 = names that appear in rows or in
+ *                nodesToRemove / nodesToAdd but not in nodesAll (never candidates);
+ *                BLANCE_NO_NODE (-1) = empty slot.
+ *   state id     index in sortStateNames(model) order (plan.go:437-447).
+ *   partition    index 0 .. n_parts-1 over keys(prevMap) U keys(partitionsToAssign).
+ *   rows         int32[n_parts][n_slots]; state s owns slots
+ *                [state_slot_off[s], state_slot_off[s+1]), filled from the left in
+ *                list order, padded with BLANCE_NO_NODE.  A state's slot range must
+ *                hold max(constraints, longest input list of that state).
+ *   shape        uint8[n_parts][n_states]: BLANCE_SHAPE_ABSENT (no such key in
+ *                NodesByState), _NIL (key present, nil slice), _LIST (non-nil slice).
+ *                reflect.DeepEqual (plan.go:38) distinguishes all three.
+ */
+#ifndef BLANCE_B200_H_
+#define BLANCE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BLANCE_NO_NODE (-1)
+
+enum blance_shape { BLANCE_SHAPE_ABSENT = 0, BLANCE_SHAPE_NIL = 1, BLANCE_SHAPE_LIST = 2 };
+
+enum blance_status {
+  BLANCE_OK = 0,
+  BLANCE_ERR_INVALID_ARG = -1,   /* malformed tables (the reference would panic or misbehave) */
+  BLANCE_ERR_UNSUPPORTED = -2,   /* e.g. a CustomNodeSorter (plan.go:580) cannot cross the ABI */
+  BLANCE_ERR_CUDA = -3,          /* no device / launch or runtime failure */
+  BLANCE_ERR_NCCL = -4,
+  BLANCE_ERR_NOMEM = -5
+};
+
+/* NodeScoreBooster (plan.go:693-697) is a Go func value and cannot cross; the
+ * only booster in the reference tree is cbgt's (control_test.go:19-26). */
+enum blance_booster { BLANCE_BOOSTER_NONE = 0, BLANCE_BOOSTER_CBGT_MAX = 1 };
+
+/* Which engine runs the sequential greedy chain of one state pass. */
+enum blance_engine {
+  BLANCE_ENGINE_AUTO = 0,
+  BLANCE_ENGINE_EXACT_CTA = 1,    /* one CTA per instance, threads over nodes */
+  BLANCE_ENGINE_EXACT_WARP = 2    /* one warp per instance (n_nodes <= 1024), used by the batch path */
+};
+
+typedef struct blance_ctx blance_ctx;   /* owns the device, streams, scratch buffers */
+
+/* device_id < 0: current device.  Replaces nothing in the reference (it has no
+ * handle); the Go shim keeps one per process/GPU. */
+int blance_ctx_create(blance_ctx** out, int device_id);
+void blance_ctx_destroy(blance_ctx* ctx);
+const char* blance_last_error(const blance_ctx* ctx);   /* ctx may be NULL: last create error */
+int blance_version(void);
+
+/* ---- PlanNextMapEx (api.go:147-157; plan.go:23-331) ------------------------ */
+typedef struct blance_plan_in {
+  int32_t n_nodes;       /* len(nodesAll) */
+  int32_t n_node_ids;    /* >= n_nodes, see "Id spaces" */
+  int32_t n_states;      /* len(model) */
+  int32_t n_parts;       /* |keys(prevMap) U keys(partitionsToAssign)| */
+  int32_t n_slots;       /* = state_slot_off[n_states] */
+  int32_t max_iters;     /* MaxIterationsPerPlan, plan.go:21 */
+  int32_t top_state;     /* topPriorityStateName, plan.go:126-132 (min priority; first in state order on ties) */
+  int32_t booster_kind;  /* enum blance_booster */
+  int32_t add_is_nil;        /* nodesToAdd == nil (plan.go:554) */
+  int32_t has_part_weights;  /* PartitionWeights != nil (plan.go:105,270,534) */
+  int32_t has_node_weights;  /* NodeWeights != nil (plan.go:675) */
+  int32_t has_hier_rules;    /* HierarchyRules != nil (plan.go:174) */
+
+  /* per state, [n_states] */
+  const int32_t* state_priority;        /* model[s].Priority */
+  const int32_t* state_constraints;     /* after ModelStateConstraints override, plan.go:308-319 */
+  const int32_t* state_slot_off;        /* [n_states+1] */
+  const int32_t* state_stickiness;      /* StateStickiness[s] */
+  const uint8_t* state_has_stickiness;  /* key present */
+
+  /* per node id, [n_node_ids] */
+  const uint8_t* node_removed;          /* in nodesToRemove */
+  const uint8_t* node_added;            /* in nodesToAdd */
+  /* per node, [n_nodes] */
+  const int32_t* node_weight;           /* NodeWeights[n] */
+  const uint8_t* node_has_weight;       /* key present */
+
+  /* per partition, [n_parts] */
+  const uint8_t* part_in_prev;          /* key of prevMap */
+  const uint8_t* part_in_assign;        /* key of partitionsToAssign */
+  const int32_t* part_weight;           /* PartitionWeights[p] */
+  const uint8_t* part_has_weight;       /* key present */
+  const int32_t* part_name_rank;        /* rank under the name rule of plan.go:519-528,512 (unique) */
+  const int32_t* prev_rows;             /* [n_parts][n_slots] prevMap rows (model states only) */
+  const uint8_t* prev_shape;            /* [n_parts][n_states] */
+  const int32_t* cur_rows;              /* [n_parts][n_slots] partitionsToAssign rows */
+  const uint8_t* cur_shape;             /* [n_parts][n_states] */
+
+  /* Weighted node counts contributed by prevMap entries under state names that
+   * are NOT in the model (they only feed nodePartitionCounts, plan.go:118-124).
+   * first = all of prevMap (iteration 1); rest = only partitions that are not
+   * being assigned (iterations >= 2, after plan.go:49-52 replaced the others).
+   * [n_nodes] each; NULL = all zero. */
+  const int32_t* extra_tot_first;
+  const int32_t* extra_tot_rest;
+
+  /* Hierarchy (plan.go:174-226, 703-774), precomputed by the host as bit sets:
+   * ie_mask[r][a] = leaves(ancestor(a, include_r)) minus leaves(ancestor(a, exclude_r))
+   * for rule r (global index) and anchor a in 0..n_node_ids, where anchor
+   * n_node_ids stands for "" (no top-priority node).  Bits 0..n_nodes-1 are node
+   * ids; bits n_nodes..n_hier_bits-1 are leaf names outside nodesAll (they only
+   * matter for the emptiness test of plan.go:746).  hier_words = ceil(n_hier_bits/32). */
+  int32_t n_rules;
+  int32_t n_hier_bits;
+  const int32_t* rule_off;              /* [n_states+1] rules of state s = [rule_off[s], rule_off[s+1]) */
+  const uint32_t* ie_mask;              /* [n_rules][n_node_ids+1][hier_words] */
+
+  int32_t engine;                       /* enum blance_engine; 0 = auto */
+} blance_plan_in;
+
+typedef struct blance_plan_out {
+  int32_t* next_rows;      /* [n_parts][n_slots]; rows of part_in_assign partitions (others: cur row copy) */
+  uint8_t* next_shape;     /* [n_parts][n_states] */
+  uint8_t* warn;           /* [n_parts][n_states] 1 = "could not meet constraints" (plan.go:231-234), last iteration only */
+  int32_t iters_run;       /* inner plans executed (plan.go:32) */
+  int32_t converged;       /* 1 if the last compare of plan.go:36-42 matched */
+  int64_t steps;           /* findBestNodes calls executed over all iterations */
+  float device_ms;         /* GPU time of the whole call (events on the ctx stream), H2D/D2H included */
+  float kernel_ms;         /* GPU time with tables resident (between the copies) */
+  float pass_ms;           /* time inside the sequential assign passes only */
+} blance_plan_out;
+
+/* Host buffers in, host buffers out.  If prevMap and partitionsToAssign must be
+ * mutated as plan.go:49-52 does, the caller copies next_rows back when
+ * iters_run >= 2 || !converged. */
+int blance_plan_next_map(blance_ctx* ctx, const blance_plan_in* in, blance_plan_out* out);
+
+/* n independent instances (multi-tenant rebalance fan-out); instance i uses
+ * in[i] / out[i].  All instances run concurrently on the device. */
+int blance_plan_next_map_batch(blance_ctx* ctx, int32_t n, const blance_plan_in* in, blance_plan_out* out);
+
+/* Device-resident variant used by benchmarks and by callers that chain plans:
+ * uploads `in` once and returns a handle; blance_plan_run() replays the whole
+ * plan on the resident tables (inputs are restored on device before each run);
+ * blance_plan_fetch() copies the result out. */
+typedef struct blance_plan blance_plan;
+int blance_plan_upload(blance_ctx* ctx, const blance_plan_in* in, blance_plan** plan);
+int blance_plan_run(blance_ctx* ctx, blance_plan* plan);
+int blance_plan_fetch(blance_ctx* ctx, blance_plan* plan, blance_plan_out* out);
+void blance_plan_free(blance_ctx* ctx, blance_plan* plan);
+
+/* ---- CalcPartitionMoves (moves.go:41-119), vectorised over partitions ------- */
+enum blance_op_kind { BLANCE_OP_ADD = 0, BLANCE_OP_DEL = 1, BLANCE_OP_PROMOTE = 2, BLANCE_OP_DEMOTE = 3 };
+#define BLANCE_OP_STATE_NONE 0xFF   /* the "" state of a del op (moves.go:87) */
+
+/* beg_rows/end_rows: [n_parts][n_slots] with the slot layout of state_slot_off
+ * ([n_states+1]).  Only the first n_visit_states states are walked as `states`
+ * (moves.go:66,92); the remaining ones still count for adds/dels (moves.go:60-64).
+ * Outputs: op_* are [n_parts][max_ops] (max_ops >= 2*n_slots is always enough),
+ * op_count[n_parts] = number of ops of each partition, in the reference's order. */
+int blance_calc_partition_moves(blance_ctx* ctx, int32_t n_parts, int32_t n_states, int32_t n_visit_states,
+                                const int32_t* state_slot_off, const int32_t* beg_rows,
+                                const int32_t* end_rows, int32_t favor_min_nodes, int32_t max_ops,
+                                int32_t* op_node, uint8_t* op_state, uint8_t* op_kind, int32_t* op_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLANCE_B200_H_ */
