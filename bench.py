@@ -1,0 +1,319 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of blance_b200 (contract: see the task statement).
+
+Metric (BASELINE.json): partition-assignments/sec on the 1 048 576-partition x
+1 024-node synthetic cluster (configs[3]: heterogeneous node + partition weights,
+stickiness, 16 nodes removed / 16 added), i.e. partitions planned per second by ONE
+complete PlanNextMapEx (all convergence iterations, plan.go:23-58).
+
+  step        one complete plan of that cluster
+  value       partitions/s with the tables resident in HBM (blance_plan_run), device
+              time from CUDA events on the library's stream, max over ranks
+  e2e         the same through blance_plan_next_map with HOST buffers: staging, H2D,
+              all kernels, D2H inside the timed region
+  roofline    of the dominant kernel k_assign_pass: algorithmic bytes per findBestNodes
+              step (16*N + (N/8)(1+R*k) + 8*slots + 12) x steps /
+              its device time, against the measured HBM copy bandwidth
+  cpu_baseline  the literal C++ restatement of the Go planner (oracle/literal.cpp: string
+              hash maps + comparison sort, the reference's asymptotics) on a bounded
+              sample of the same cluster shape, 1 core (the reference planner is
+              single-goroutine).  Go itself cannot run here (no toolchain).
+
+--gpus N: the greedy chain of one plan is sequential (each step reads the counts the
+previous step wrote), so one plan does not shard; N ranks plan N independent clusters
+of the named shape (distinct seeds) — "replicas only", weak scaling, no collective in
+the data path; torch.distributed(nccl) is used for the barrier and the max over ranks.
+
+--impl reference: the CPU arm — the literal oracle on the box's host cores (rank 0 only).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CFG = 4
+METRIC = "partition-assignments/sec, 1M parts x 1024 nodes (partitions planned per second by one complete PlanNextMapEx)"
+UNIT = "partitions/s"
+
+
+def b_alg(n_nodes, n_rules, k, slots):
+    return 16 * n_nodes + (n_nodes // 8) * (1 + n_rules * k) + 8 * slots + 12
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                pass
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_literal_sample(parts, seed_offset=0):
+    """The literal oracle on a cfg-4-shaped cluster with `parts` partitions x 1024 nodes,
+    one inner plan (per-step cost does not depend on the partition count, only the two
+    O(P log P) partition sorts do).  Returns (findBestNodes steps, seconds)."""
+    from oracle_loader import literal
+    from blance_b200 import synth
+    L = literal()
+    t = synth.make_rebalance(CFG, P=parts, seed_offset=seed_offset)
+    kw = synth.to_dicts(t, CFG)
+    kw["max_iterations"] = 1
+    r = L.plan_next_map_ex(**kw)
+    return r["steps"], r["seconds"]
+
+
+def cpu_fast_sample(parts):
+    import ctypes
+    from oracle_loader import fast_lib_path
+    from blance_b200 import synth, tables
+    fast = ctypes.CDLL(fast_lib_path())
+    fast.oracle_fast_plan_next_map.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    t = synth.make_rebalance(CFG, P=parts)
+    t.max_iters = 1
+    r = tables.PlanResult(t)
+    s = t.struct()
+    t0 = time.perf_counter()
+    fast.oracle_fast_plan_next_map(ctypes.byref(s), ctypes.byref(r.out))
+    return r.steps, time.perf_counter() - t0
+
+
+def workload_facts():
+    """Deterministic properties of the benchmark cluster, recorded by the GPU arm
+    (profiles/workload_cfg4.json) so the CPU arm can convert steps/s to partitions/s."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "workload_cfg4.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    facts = workload_facts()
+    spp = facts["steps_per_partition"] if facts else None
+    sample_parts = args.cpu_sample_parts
+    times, steps = [], 0
+    for i in range(args.warmup + args.steps):
+        st, sec = cpu_literal_sample(sample_parts, seed_offset=i)
+        if i >= args.warmup:
+            times.append(sec)
+            steps += st
+    total = sum(times)
+    steps_per_s = steps / total
+    value = steps_per_s / spp if spp else None
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64 score / int32 tables", "data": "synthetic",
+        "config": {"workload": "cfg4: PlanNextMapEx 1048576 partitions x 1024 nodes, k=(1,2), node+partition weights, "
+                               "stickiness, -16/+16 nodes", "steps_per_partition": spp,
+                   "parallelism": "1 host core (the reference planner is single-goroutine)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                         "findBestNodes_steps_per_s": steps_per_s,
+                         "sample": "literal C++ restatement of the Go planner (oracle/literal.cpp); each step = one inner plan "
+                                   "of a %d-partition x 1024-node cluster of the cfg4 shape; partitions/s = measured "
+                                   "findBestNodes steps/s / %s steps per partition of the full workload (per-step cost is "
+                                   "flat in the partition count)" % (sample_parts, spp)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="blance_b200")
+    ap.add_argument("--parts", type=int, default=None, help="override the partition count (debug only; invalidates the headline)")
+    ap.add_argument("--cpu-sample-parts", type=int, default=1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    from blance_b200 import synth, tables
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    t = synth.make_rebalance(CFG, P=args.parts, seed_offset=rank)
+    ctx = tables.Context(local_rank)
+    plan = ctx.upload(t)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > L2 (126 MB)
+
+    for _ in range(max(args.warmup, 3)):
+        ctx.run(plan)
+    res = ctx.fetch(plan, tables.PlanResult(t))
+    steps_per_plan, iters = int(res.steps), int(res.iters_run)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.start()
+    launches0 = ctx.kernel_launches()
+    kernel_ms, pass_ms, pass_launches = [], [], 0
+    for _ in range(args.steps):
+        flush.zero_()                       # L2 flush between timed iterations (not timed)
+        torch.cuda.synchronize()
+        ctx.run(plan)
+        k, p, n = ctx.timing(plan)
+        kernel_ms.append(k)
+        pass_ms.append(p)
+        pass_launches += n
+    barrier()
+    launches = ctx.kernel_launches() - launches0
+    clocks = sampler.stop() if sampler else None
+    total_ms = sum(kernel_ms)
+    tt = torch.tensor([total_ms, sum(pass_ms)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms_max, pass_ms_max = float(tt[0]), float(tt[1])
+
+    # ---- end to end through the C ABI with host buffers -----------------------------------
+    h2d = sum(np.asarray(getattr(t, f)).nbytes for f in
+              ("prev_rows", "cur_rows", "prev_shape", "cur_shape", "part_in_prev", "part_in_assign", "part_weight",
+               "part_has_weight", "part_name_rank", "node_removed", "node_added", "node_weight", "node_has_weight",
+               "extra_tot_first", "extra_tot_rest", "ie_mask"))
+    out = tables.PlanResult(t)
+    d2h = out.next_rows.nbytes + out.next_shape.nbytes + out.warn.nbytes
+    ctx.plan_next_map(t, out)               # warm-up of the e2e path
+    barrier()
+    e2e_s = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        ctx.plan_next_map(t, out)
+        e2e_s.append(time.perf_counter() - t0)
+    barrier()
+    te = torch.tensor([sum(e2e_s)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_total = float(te[0])
+    same = bool(np.array_equal(out.next_rows, res.next_rows))
+
+    if rank == 0:
+        P, N = t.n_parts, t.n_nodes
+        value = world * P * args.steps / (total_ms_max / 1e3)
+        e2e_value = world * P * args.steps / e2e_total
+        bytes_per_step = b_alg(N, 0, 2, t.n_slots)
+        peak, peak_src = measured_peak()
+        pass_s = pass_ms_max / 1e3
+        achieved = steps_per_plan * args.steps * bytes_per_step / pass_s / 1e9 if pass_s > 0 else None
+        os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
+        if args.parts is None:
+            try:
+                with open(os.path.join(ROOT, "profiles", "workload_cfg4.json"), "w") as f:
+                    json.dump({"workload": "cfg4", "n_parts": P, "n_nodes": N, "iterations": iters,
+                               "findBestNodes_steps": steps_per_plan, "steps_per_partition": steps_per_plan / P}, f)
+            except OSError:
+                pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64 score / int32 tables", "data": "synthetic",
+            "config": {"workload": "cfg4: PlanNextMapEx %d partitions x %d nodes, k=(1,2), node+partition weights, stickiness, "
+                                   "-16/+16 nodes; one step = one complete plan (%d convergence iterations, %d findBestNodes steps)"
+                                   % (P, N, iters, steps_per_plan),
+                       "steps_per_partition": steps_per_plan / P,
+                       "parallelism": "replicas only: %d independent plan(s), one per GPU; no data-path collective" % world,
+                       "l2": "256 MiB device buffer rewritten between timed iterations (L2 flush)",
+                       "timing": "CUDA events on the library stream, max over ranks"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1e3 * e2e_total / args.steps, "result_equals_resident_run": same},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_assign_pass", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "peak_source": peak_src, "bytes_per_findBestNodes_step": bytes_per_step,
+                         "steps_per_launch": steps_per_plan * args.steps / max(1, pass_launches),
+                         "t_step_ns": 1e9 * pass_s / (steps_per_plan * args.steps),
+                         "note": "the pass is a loop-carried dependency chain (latency bound), not a streaming kernel; "
+                                 "see DESIGN.md"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            st, sec = cpu_literal_sample(args.cpu_sample_parts)
+            spp = steps_per_plan / P
+            fst, fsec = cpu_fast_sample(32768)
+            line["cpu_baseline"] = {
+                "value": st / sec / spp, "unit": UNIT, "cores": 1, "kind": "port",
+                "findBestNodes_steps_per_s": st / sec,
+                "sample": "literal C++ restatement of the Go planner (oracle/literal.cpp) on one inner plan of a %d-partition x "
+                          "%d-node cluster of the same shape (%d findBestNodes steps, %.1f s); partitions/s = steps/s / %.1f steps "
+                          "per partition of the full workload" % (args.cpu_sample_parts, N, st, sec, spp),
+                "best_cpu_array_oracle": {"value": fst / fsec / spp, "unit": UNIT, "findBestNodes_steps_per_s": fst / fsec,
+                                          "sample": "oracle/fast.c, 32768 x %d, one inner plan" % N}}
+        print(json.dumps(line), flush=True)
+    ctx.free(plan)
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

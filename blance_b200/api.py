@@ -106,8 +106,8 @@ class _PlanOut(ctypes.Structure):
 
 
 _CAPI = None
-EXPORTS = ("blance_ctx_create", "blance_ctx_destroy", "blance_last_error", "blance_version", "blance_plan_next_map",
-           "blance_plan_next_map_batch", "blance_plan_upload", "blance_plan_run", "blance_plan_fetch", "blance_plan_free",
+EXPORTS = ("blance_ctx_create", "blance_ctx_destroy", "blance_last_error", "blance_version", "blance_ctx_kernel_launches", "blance_plan_next_map",
+           "blance_plan_next_map_batch", "blance_plan_upload", "blance_plan_run", "blance_plan_fetch", "blance_plan_free", "blance_plan_timing",
            "blance_calc_partition_moves")
 
 
@@ -122,11 +122,15 @@ def capi():
         lib.blance_ctx_destroy.restype = None
         lib.blance_last_error.argtypes = [vp]
         lib.blance_last_error.restype = ctypes.c_char_p
+        lib.blance_ctx_kernel_launches.argtypes = [vp]
+        lib.blance_ctx_kernel_launches.restype = ctypes.c_int64
         lib.blance_plan_next_map.argtypes = [vp, vp, vp]
         lib.blance_plan_next_map_batch.argtypes = [vp, i32, vp, vp]
         lib.blance_plan_upload.argtypes = [vp, vp, ctypes.POINTER(vp)]
         lib.blance_plan_run.argtypes = [vp, vp]
         lib.blance_plan_fetch.argtypes = [vp, vp, vp]
+        lib.blance_plan_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float),
+                                           ctypes.POINTER(ctypes.c_int32)]
         lib.blance_plan_free.argtypes = [vp, vp]
         lib.blance_plan_free.restype = None
         lib.blance_calc_partition_moves.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, i32, vp, vp, vp, vp]

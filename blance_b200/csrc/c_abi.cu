@@ -35,6 +35,7 @@ struct blance_ctx {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   int* d_any_active = nullptr;
   int* h_any_active = nullptr;       // pinned
+  long long launches = 0;            // kernels of this library launched so far
 };
 
 #define CK(call)                                                                           \
@@ -54,6 +55,8 @@ static int fail(blance_ctx* ctx, int st, const std::string& msg) {
 }
 
 extern "C" int blance_version(void) { return 100; }
+
+extern "C" int64_t blance_ctx_kernel_launches(const blance_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 extern "C" const char* blance_last_error(const blance_ctx* ctx) {
   return ctx ? ctx->err.c_str() : g_create_error.c_str();
@@ -160,8 +163,9 @@ static int validate(blance_ctx* ctx, const blance_plan_in* in, int idx) {
       return bad("a state's slot range is smaller than its constraints");
   }
   if (in->n_parts > 0 && (!in->part_in_prev || !in->part_in_assign || !in->part_weight || !in->part_has_weight ||
-                          !in->part_name_rank || !in->prev_shape || !in->cur_shape))
+                          !in->part_name_rank))
     return bad("partition tables are NULL");
+  if (in->n_parts > 0 && in->n_states > 0 && (!in->prev_shape || !in->cur_shape)) return bad("shape tables are NULL");
   if (in->n_parts > 0 && in->n_slots > 0 && (!in->prev_rows || !in->cur_rows)) return bad("row tables are NULL");
   if (in->n_node_ids > 0 && (!in->node_removed || !in->node_added)) return bad("node flag tables are NULL");
   if (in->n_nodes > 0 && in->has_node_weights && (!in->node_weight || !in->node_has_weight)) return bad("node weight tables are NULL");
@@ -364,6 +368,7 @@ static int upload(blance_ctx* ctx, int n, const blance_plan_in* ins, blance_plan
   if (pl->PT > 0) {
     k_unpack<<<grid_for(ctx, pl->PT, 256), 256, 0, st>>>(P, pl->raw_a, pl->raw_b, pl->rawsh_a, pl->rawsh_b,
                                                         pl->d_raw_rows_off, pl->d_raw_shape_off, pl->PT);
+    ctx->launches++;
     e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(pl->rows_init, P.rows, sizeof(int32_t) * (size_t)pl->RT, cudaMemcpyDeviceToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(pl->prev_rows_init, P.prev_rows, sizeof(int32_t) * (size_t)pl->RT, cudaMemcpyDeviceToDevice, st);
@@ -431,9 +436,16 @@ static int run(blance_ctx* ctx, blance_plan* pl) {
   pl->pass_launches = 0;
   const bool smem_hist = (n == 1) && ((size_t)pl->h_insts[0].S * pl->h_insts[0].N * sizeof(int32_t) <= 40 * 1024);
   int guard = 0;
-  while (any_active > 0 && pl->PT > 0) {
+  while (any_active > 0) {
     if (++guard > 100000) return fail(ctx, BLANCE_ERR_CUDA, "convergence loop did not terminate");
+    if (pl->PT == 0) {          // no partitions at all: the loop of plan.go:32-45 still runs once and matches
+      CK(cudaMemsetAsync(ctx->d_any_active, 0, sizeof(int), st));
+      k_next_iter<<<(n + 127) / 128, 128, 0, st>>>(P, n, ctx->d_any_active);
+      ctx->launches++;
+      break;
+    }
     k_prepare_rows<<<grid, blk, 0, st>>>(P, pl->PT);
+    ctx->launches += 2;   // + k_count_prev below
     CK(cudaMemsetAsync(P.counts, 0, sizeof(int32_t) * (size_t)(pl->CT + 1), st));
     if (smem_hist)
       k_count_prev<true><<<std::min(grid, ctx->sm_count * 2), blk, (size_t)pl->h_insts[0].S * pl->h_insts[0].N * sizeof(int32_t), st>>>(P, pl->PT);
@@ -442,6 +454,7 @@ static int run(blance_ctx* ctx, blance_plan* pl) {
     for (int s = 0; s < pl->max_S; ++s) {
       if (!pl->any_state_active[s]) continue;
       k_build_keys<<<grid, blk, 0, st>>>(P, s, pl->PT);
+      ctx->launches += 2;   // + k_assign_pass below
       size_t tmp = ctx->cub_tmp_bytes;
       if (n == 1)
         CK(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp, tmp, P.keys_alt, P.keys, P.order_alt, P.order, (int)pl->PT, 0, 64, st));
@@ -462,6 +475,7 @@ static int run(blance_ctx* ctx, blance_plan* pl) {
       pl->pass_launches++;
     }
     k_compare<<<grid, blk, 0, st>>>(P, pl->PT);
+    ctx->launches += 3;   // + k_commit, k_next_iter
     k_commit<<<grid, blk, 0, st>>>(P, pl->PT);
     CK(cudaMemsetAsync(ctx->d_any_active, 0, sizeof(int), st));
     k_next_iter<<<(n + 127) / 128, 128, 0, st>>>(P, n, ctx->d_any_active);
@@ -492,6 +506,7 @@ static int fetch(blance_ctx* ctx, blance_plan* pl, blance_plan_out* outs) {
     k_pack<<<grid_for(ctx, pl->PT, 256), 256, 0, st>>>(pl->pool, pl->raw_a, pl->rawsh_a, pl->rawsh_b, pl->d_raw_rows_off,
                                                       pl->d_raw_shape_off, pl->PT);
     CK(cudaGetLastError());
+    ctx->launches++;
   }
   // results land in the pinned staging buffer (its head is large enough: it held cur+prev rows)
   char* hp = (char*)pl->h_stage;
@@ -542,6 +557,14 @@ extern "C" int blance_plan_fetch(blance_ctx* ctx, blance_plan* plan, blance_plan
   if (!ctx || !plan || !out) return fail(ctx, BLANCE_ERR_INVALID_ARG, "ctx, plan or out is NULL");
   std::lock_guard<std::mutex> g(ctx->mu);
   return fetch(ctx, plan, out);
+}
+
+extern "C" int blance_plan_timing(const blance_plan* plan, float* kernel_ms, float* pass_ms, int32_t* pass_launches) {
+  if (!plan) return BLANCE_ERR_INVALID_ARG;
+  if (kernel_ms) *kernel_ms = plan->last_kernel_ms;
+  if (pass_ms) *pass_ms = plan->last_pass_ms;
+  if (pass_launches) *pass_launches = plan->pass_launches;
+  return BLANCE_OK;
 }
 
 extern "C" void blance_plan_free(blance_ctx* ctx, blance_plan* plan) {
@@ -616,6 +639,7 @@ extern "C" int blance_calc_partition_moves(blance_ctx* ctx, int32_t n_parts, int
                                                              favor_min_nodes, max_ops, (int32_t*)(d + o_node),
                                                              (uint8_t*)(d + o_state), (uint8_t*)(d + o_kind), (int32_t*)(d + o_cnt));
     step(cudaGetLastError(), "k_calc_moves");
+    ctx->launches++;
   }
   if (max_ops > 0) {
     step(cudaMemcpyAsync(op_node, d + o_node, sizeof(int32_t) * (size_t)n_parts * max_ops, cudaMemcpyDeviceToHost, st), "D2H");

@@ -143,6 +143,12 @@ class Context:
     def run(self, plan):
         self._check(self.lib.blance_plan_run(self.ptr, plan), "blance_plan_run")
 
+    def timing(self, plan):
+        """(kernel_ms, pass_ms, pass_launches) of the last run()."""
+        k, p, n = ctypes.c_float(), ctypes.c_float(), ctypes.c_int32()
+        self._check(self.lib.blance_plan_timing(plan, ctypes.byref(k), ctypes.byref(p), ctypes.byref(n)), "blance_plan_timing")
+        return k.value, p.value, n.value
+
     def fetch(self, plan, result):
         self._check(self.lib.blance_plan_fetch(self.ptr, plan, ctypes.byref(result.out)), "blance_plan_fetch")
         return result
@@ -167,6 +173,9 @@ class Context:
             op_state.ctypes.data, op_kind.ctypes.data, op_count.ctypes.data)
         self._check(st, "blance_calc_partition_moves")
         return op_node, op_state, op_kind, op_count
+
+    def kernel_launches(self):
+        return int(self.lib.blance_ctx_kernel_launches(self.ptr))
 
     def close(self):
         if self.ptr:

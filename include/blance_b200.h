@@ -71,6 +71,9 @@ int blance_ctx_create(blance_ctx** out, int device_id);
 void blance_ctx_destroy(blance_ctx* ctx);
 const char* blance_last_error(const blance_ctx* ctx);   /* ctx may be NULL: last create error */
 int blance_version(void);
+/* Number of libblance_b200 kernels launched on this context since it was created
+ * (the sort library's own kernels are not counted). */
+int64_t blance_ctx_kernel_launches(const blance_ctx* ctx);
 
 /* ---- PlanNextMapEx (api.go:147-157; plan.go:23-331) ------------------------ */
 typedef struct blance_plan_in {
@@ -164,6 +167,10 @@ int blance_plan_upload(blance_ctx* ctx, const blance_plan_in* in, blance_plan** 
 int blance_plan_run(blance_ctx* ctx, blance_plan* plan);
 int blance_plan_fetch(blance_ctx* ctx, blance_plan* plan, blance_plan_out* out);
 void blance_plan_free(blance_ctx* ctx, blance_plan* plan);
+/* Device times of the last blance_plan_run (CUDA events on the ctx stream): the whole
+ * run, the part spent inside the sequential assign-pass kernels, and how many of
+ * those were launched. */
+int blance_plan_timing(const blance_plan* plan, float* kernel_ms, float* pass_ms, int32_t* pass_launches);
 
 /* ---- CalcPartitionMoves (moves.go:41-119), vectorised over partitions ------- */
 enum blance_op_kind { BLANCE_OP_ADD = 0, BLANCE_OP_DEL = 1, BLANCE_OP_PROMOTE = 2, BLANCE_OP_DEMOTE = 3 };
