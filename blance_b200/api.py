@@ -115,7 +115,8 @@ def capi():
     """ctypes handle of libblance_b200.so with argtypes set (the same symbols a cgo shim binds)."""
     global _CAPI
     if _CAPI is None:
-        lib = ctypes.CDLL(_build.lib_path())
+        import os
+        lib = ctypes.CDLL(os.environ.get("BLANCE_B200_LIB", _build.lib_path()))   # override: instrumented builds
         vp, i32 = ctypes.c_void_p, ctypes.c_int32
         lib.blance_ctx_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int]
         lib.blance_ctx_destroy.argtypes = [vp]

@@ -156,6 +156,92 @@ __global__ void k_build_keys(DPool pool, int s, long long n_parts_total) {
   }
 }
 
+// ---- step stream of a pass: records in the sorted order, so the sequential kernel reads linearly -----
+// record i of an instance (SLP + 8 words), pre-decoded so the chain does no per-step decoding:
+//   row[SLP] | meta, w_p, top, partition | stickiness (double), 2 spare words
+// w_p = partition weight (plan.go:269-275), stickiness per plan.go:104-115, top = first node of the
+// top-priority state or NU for "" (plan.go:134-138).
+__global__ void k_gather_stream(DPool pool, int s, long long n_parts_total) {
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n_parts_total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const DInst& D = pool.insts[pool.part_inst[g]];
+    if (!D.active || s >= D.S || D.state_constraints[s] <= 0) continue;
+    const long long i = g - D.part_off;                 // step index inside the instance
+    if (i >= D.n_assign) continue;
+    const int32_t p = pool.order[g];
+    const int REC = D.SLP + 8;
+    int32_t* dst = pool.stream + D.stream_off + i * REC;
+    const int32_t* row = pool.rows + D.rows_off + (long long)p * D.SLP;
+    for (int t = 0; t < D.SLP; ++t) dst[t] = row[t];
+    const uint8_t f = pool.pflags[D.part_off + p];
+    int32_t w_p = 1;
+    double stick = 1.5;
+    if (D.has_part_weights) {
+      if (f & PF_HAS_WEIGHT) { w_p = pool.pweight[D.part_off + p]; stick = (double)w_p; }
+      else if (D.state_has_stickiness[s]) stick = (double)D.state_stickiness[s];
+    }
+    int32_t top = D.NU;
+    const int ts = D.state_slot_off[D.top_state];
+    if (D.state_slot_off[D.top_state + 1] > ts && row[ts] != BLANCE_NO_NODE) top = row[ts];
+    dst[D.SLP] = (int32_t)pool.pmeta[D.part_off + p];
+    dst[D.SLP + 1] = w_p;
+    dst[D.SLP + 2] = top;
+    dst[D.SLP + 3] = p;
+    const long long sb = __double_as_longlong(stick);
+    dst[D.SLP + 4] = (int32_t)(sb & 0xFFFFFFFFll);
+    dst[D.SLP + 5] = (int32_t)(sb >> 32);
+    dst[D.SLP + 6] = 0;
+    dst[D.SLP + 7] = 0;
+  }
+}
+
+// After the pass: rebuild every partition's row from the step's outcome (plan.go:290-301), in
+// parallel.  ostream record i = { chosen[0..k), n_chosen }; stream record i still
+// holds the row / meta / partition the step started from.
+__global__ void k_scatter_stream(DPool pool, int s, long long n_parts_total) {
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n_parts_total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const DInst& D = pool.insts[pool.part_inst[g]];
+    if (!D.active || s >= D.S || D.state_constraints[s] <= 0) continue;
+    const long long i = g - D.part_off;
+    if (i >= D.n_assign) continue;
+    const int REC = D.SLP + 8, k = D.state_constraints[s];
+    const int32_t* in = pool.stream + D.stream_off + i * REC;
+    const int32_t* out = pool.ostream + D.stream_off + i * REC;
+    const int32_t p = in[D.SLP + 3];
+    const uint32_t meta = (uint32_t)in[D.SLP];
+    const int n_chosen = out[k];
+    const int lo_s = D.state_slot_off[s], hi_s = D.state_slot_off[s + 1];
+    int32_t* row = pool.rows + D.rows_off + (long long)p * D.SLP;
+    uint32_t nmeta = meta;
+    bool have_higher_key = false;
+    for (int s2 = 0; s2 < D.S; ++s2) {
+      if (meta_shape(meta, s2) == BLANCE_SHAPE_ABSENT) continue;
+      if (D.state_priority[s2] < D.state_priority[s]) have_higher_key = true;
+      if (s2 == s) continue;
+      nmeta = meta_set_shape(nmeta, s2, BLANCE_SHAPE_LIST);          // misc.go:29: non-nil after removal
+      int o = D.state_slot_off[s2];
+      const int e = D.state_slot_off[s2 + 1];
+      for (int sl = o; sl < e; ++sl) {                               // removeNodesFromNodesByState x2
+        const int32_t x = in[sl];
+        if (x == BLANCE_NO_NODE) break;
+        bool rm = false;
+        for (int q = lo_s; q < hi_s && in[q] != BLANCE_NO_NODE; ++q) rm |= (in[q] == x);
+        for (int c = 0; c < n_chosen; ++c) rm |= (out[c] == x);
+        if (!rm) row[o++] = x;
+      }
+      for (; o < e; ++o) row[o] = BLANCE_NO_NODE;
+    }
+    for (int sl = lo_s; sl < hi_s; ++sl) row[sl] = (sl - lo_s) < n_chosen ? out[sl - lo_s] : BLANCE_NO_NODE;   // plan.go:299
+    // nil result: candidateNodes stays nil only if nodesNext is empty, no higher-priority key filtered
+    // it and the hierarchy block did not run (plan.go:142,149-150,225)
+    const bool nil = n_chosen == 0 && D.n_valid == 0 && !have_higher_key && !D.has_hier_rules;
+    nmeta = meta_set_shape(nmeta, s, nil ? BLANCE_SHAPE_NIL : BLANCE_SHAPE_LIST);
+    if (n_chosen < k) nmeta |= 1u << (16 + s);                       // plan.go:228-235
+    pool.pmeta[D.part_off + p] = nmeta;
+  }
+}
+
 // ---- convergence test (plan.go:36-42) -------------------------------------------------------------
 __global__ void k_compare(DPool pool, long long n_parts_total) {
   for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n_parts_total;

@@ -115,7 +115,7 @@ struct blance_plan {
   int n_inst = 0;
   std::vector<DInst> h_insts;          // initial descriptors (dynamic fields at their start values)
   std::vector<long long> raw_rows_off, raw_shape_off;   // caller-layout offsets per instance
-  long long PT = 0, RT = 0, NT = 0, NUT = 0, CT = 0, N2T = 0, MT = 0, RRT = 0, RST = 0;
+  long long PT = 0, RT = 0, NT = 0, NUT = 0, CT = 0, N2T = 0, MT = 0, RRT = 0, RST = 0, ST = 0;
   int max_N = 0, max_S = 0;
   bool any_state_active[BL_S_MAX] = {};
   void* arena = nullptr;               // one device allocation, carved below
@@ -150,7 +150,7 @@ static int validate(blance_ctx* ctx, const blance_plan_in* in, int idx) {
     return bad("negative size or n_node_ids < n_nodes");
   if (in->n_states > BL_S_MAX) return bad("more than 8 model states", BLANCE_ERR_UNSUPPORTED);
   if (in->n_slots > BL_SLP_MAX) return bad("more than 32 slots per row", BLANCE_ERR_UNSUPPORTED);
-  if (in->n_nodes > 8192) return bad("more than 8192 nodes", BLANCE_ERR_UNSUPPORTED);
+  if (in->n_nodes > 8192) return bad("more than 8192 nodes", BLANCE_ERR_UNSUPPORTED);   /* 512 compute threads x 16 nodes */
   if (in->n_states > 0 && (!in->state_priority || !in->state_constraints || !in->state_slot_off ||
                            !in->state_stickiness || !in->state_has_stickiness))
     return bad("state tables are NULL");
@@ -243,9 +243,10 @@ static int upload(blance_ctx* ctx, int n, const blance_plan_in* ins, blance_plan
     D.P = n_prev; D.rm_active = rm_active; D.add_active = 1; D.add_is_nil = in.add_is_nil; D.use_rest = 0;
     D.active = in.max_iters > 0 ? 1 : 0;
     D.part_off = pl->PT; D.rows_off = pl->RT; D.node_off = pl->NT; D.nodeid_off = pl->NUT;
-    D.counts_off = pl->CT; D.n2n_off = pl->N2T; D.mask_off = pl->MT;
+    D.counts_off = pl->CT; D.n2n_off = pl->N2T; D.mask_off = pl->MT; D.stream_off = pl->ST;
     pl->raw_rows_off[i] = pl->RRT; pl->raw_shape_off[i] = pl->RST;
     seg_off[i] = (int)pl->PT;
+    pl->ST += (long long)D.PU * (D.SLP + 8);
     pl->PT += D.PU; pl->RT += (long long)D.PU * D.SLP; pl->NT += D.N; pl->NUT += D.NU;
     pl->CT += (long long)D.S * D.N; pl->N2T += (long long)(D.NU + 1) * D.N;
     pl->MT += (long long)D.n_rules * (D.NU + 1) * D.HW;
@@ -271,6 +272,7 @@ static int upload(blance_ctx* ctx, int n, const blance_plan_in* ins, blance_plan
   SL_(P.pmeta, uint32_t, PT); SL_(P.prev_meta, uint32_t, PT); SL_(pl->pmeta_init, uint32_t, PT); SL_(pl->prev_meta_init, uint32_t, PT);
   SL_(P.pflags, uint8_t, PT); SL_(pl->pflags_init, uint8_t, PT);
   SL_(c_pweight, int32_t, PT); SL_(c_rank, int32_t, PT); SL_(c_inst, int32_t, PT);
+  SL_(P.stream, int32_t, (size_t)pl->ST + 4); SL_(P.ostream, int32_t, (size_t)pl->ST + 4);
   SL_(P.keys, unsigned long long, PT); SL_(P.keys_alt, unsigned long long, PT); SL_(P.order, int32_t, PT); SL_(P.order_alt, int32_t, PT);
   SL_(c_rm, uint8_t, NUT); SL_(c_ad, uint8_t, NUT); SL_(c_nw, int32_t, NT); SL_(c_hw, uint8_t, NT);
   SL_(c_ef, int32_t, NT); SL_(c_er, int32_t, NT);
@@ -404,9 +406,26 @@ static cudaEvent_t get_event(blance_ctx* ctx, size_t idx) {
   return ctx->events[idx];
 }
 
-template <int NPT>
-static void launch_pass(const DPool& P, int n_inst, int T, int s, cudaStream_t st) {
-  k_assign_pass<NPT><<<n_inst, T, 0, st>>>(P, s);
+template <int NPT, int MAXT>
+static void launch_pass(const DPool& P, int n_inst, int T, int s, bool hier, cudaStream_t st) {
+  if (hier) k_assign_pass<NPT, true, MAXT><<<n_inst, T, 0, st>>>(P, s);
+  else k_assign_pass<NPT, false, MAXT><<<n_inst, T, 0, st>>>(P, s);
+}
+
+static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+// Compute threads per CTA (TC, a power of two; the kernel adds one service warp) and nodes per
+// thread for the pass kernel.  The chain is latency bound, so prefer many warps with few nodes each.
+static void pass_shape(int max_n, int* TC, int* npt) {
+  int want = max_n > 512 ? 2 : 1;
+  if (const char* e = getenv("BLANCE_PASS_NPT")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) want = v; }
+  if (max_n > 3968) want = 8;
+  int t = next_pow2((std::max(1, max_n) + want - 1) / want);
+  if (t < 32) t = 32;
+  if (t > 512) t = 512;
+  int n = (max_n + t - 1) / t;
+  *npt = n <= 1 ? 1 : n <= 2 ? 2 : n <= 4 ? 4 : n <= 8 ? 8 : 16;
+  *TC = t;
 }
 
 static int run(blance_ctx* ctx, blance_plan* pl) {
@@ -425,9 +444,10 @@ static int run(blance_ctx* ctx, blance_plan* pl) {
   CK(cudaMemcpyAsync(P.insts, pl->h_insts.data(), sizeof(DInst) * (size_t)n, cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(ctx->ev[1], st));
 
-  int T = std::min(1024, (int)align_up((size_t)std::max(1, pl->max_N), 32));
-  int npt = (pl->max_N + T - 1) / T;
-  if (npt < 1) npt = 1;
+  int T = 32, npt = 1;
+  pass_shape(pl->max_N, &T, &npt);
+  bool any_hier = false;
+  for (int i = 0; i < n; ++i) any_hier |= pl->h_insts[i].has_hier_rules != 0;
   int any_active = 0;
   for (int i = 0; i < n; ++i) any_active += pl->h_insts[i].active;
   const int blk = 256;
@@ -461,18 +481,20 @@ static int run(blance_ctx* ctx, blance_plan* pl) {
       else
         CK(cub::DeviceSegmentedRadixSort::SortPairs(ctx->cub_tmp, tmp, P.keys_alt, P.keys, P.order_alt, P.order, (int)pl->PT,
                                                     n, pl->d_seg_off, pl->d_seg_off + 1, 0, 64, st));
+      k_gather_stream<<<grid, blk, 0, st>>>(P, s, pl->PT);
       CK(cudaMemsetAsync(P.n2n, 0, sizeof(int32_t) * (size_t)(pl->N2T + 1), st));     // plan.go:266
       cudaEvent_t e0 = get_event(ctx, n_ev), e1 = get_event(ctx, n_ev + 1);
       if (e0 && e1 && n_ev < 256) CK(cudaEventRecord(e0, st));
-      switch (npt) {
-        case 1: launch_pass<1>(P, n, T, s, st); break;
-        case 2: launch_pass<2>(P, n, T, s, st); break;
-        case 3: case 4: launch_pass<4>(P, n, T, s, st); break;
-        default: launch_pass<8>(P, n, T, s, st); break;
-      }
+      if (npt == 1) launch_pass<1, 544>(P, n, T + 32, s, any_hier, st);
+      else if (npt == 2) launch_pass<2, 544>(P, n, T + 32, s, any_hier, st);
+      else if (npt == 4) launch_pass<4, 544>(P, n, T + 32, s, any_hier, st);
+      else if (npt == 8) launch_pass<8, 544>(P, n, T + 32, s, any_hier, st);
+      else launch_pass<16, 544>(P, n, T + 32, s, any_hier, st);
       CK(cudaGetLastError());
       if (e0 && e1 && n_ev < 256) { CK(cudaEventRecord(e1, st)); n_ev += 2; }
       pl->pass_launches++;
+      k_scatter_stream<<<grid, blk, 0, st>>>(P, s, pl->PT);
+      ctx->launches += 2;   // gather + scatter
     }
     k_compare<<<grid, blk, 0, st>>>(P, pl->PT);
     ctx->launches += 3;   // + k_commit, k_next_iter

@@ -11,6 +11,8 @@
 //   pflags             uint8 [sum PU_i]          IN_PREV | IN_ASSIGN | HAS_WEIGHT
 //   pweight, name_rank int32 [sum PU_i]
 //   keys / order       uint64 / int32 [sum PU_i] partition sort key and permutation
+//   stream / ostream   int32 [sum PU_i][SLP_i+8] the pass's input / output records in STEP order
+//                                                (row | meta, w_p, top, partition | stickiness)
 //   counts             int32 [S_i][N_i]          stateNodeCounts (plan.go:92-94)
 //   n2n                int32 [NU_i+1][N_i]       nodeToNodeCounts (plan.go:266), row NU = ""
 //   ie_mask            uint32[R_i][NU_i+1][HW_i] hierarchy include/exclude bit sets
@@ -34,7 +36,7 @@ struct DInst {
   int32_t state_priority[BL_S_MAX], state_constraints[BL_S_MAX], state_slot_off[BL_S_MAX + 1];
   int32_t state_stickiness[BL_S_MAX], state_has_stickiness[BL_S_MAX], rule_off[BL_S_MAX + 1];
   // offsets (in elements) into the pooled arrays
-  int64_t part_off, rows_off, node_off, nodeid_off, counts_off, n2n_off, mask_off;
+  int64_t part_off, rows_off, node_off, nodeid_off, counts_off, n2n_off, mask_off, stream_off;
   // dynamic state of the convergence loop (plan.go:32-56)
   int32_t P;               // len(prevMap) seen by this iteration (plan.go:161)
   int32_t rm_active;       // len(nodesToRemove) > 0 (iteration 1 only, plan.go:54)
@@ -54,6 +56,7 @@ struct DPool {
   const int32_t* pweight; const int32_t* name_rank; const int32_t* part_inst;
   unsigned long long* keys; unsigned long long* keys_alt;
   int32_t* order; int32_t* order_alt;
+  int32_t* stream; int32_t* ostream;      // step records in / out, [sum PU_i][SLP_i + 8], in step order
   // per node / node id
   const uint8_t* node_removed; const uint8_t* node_added;     // [NU]
   const int32_t* node_weight; const uint8_t* node_has_weight; // [N]
