@@ -125,6 +125,17 @@ def cpu_fast_sample(parts):
     return r.steps, time.perf_counter() - t0
 
 
+def ncu_traffic(steps_per_launch):
+    """DRAM bytes per k_assign_pass launch from the committed ncu --set full capture
+    (profiles/ncu_traffic.json: dram read+write bytes per step of one captured launch), scaled to
+    the bench's steps per launch; None when no capture is committed."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return float(json.load(f)["dram_bytes_per_step"]) * steps_per_launch
+    except Exception:
+        return None
+
+
 def workload_facts():
     """Deterministic properties of the benchmark cluster, recorded by the GPU arm
     (profiles/workload_cfg4.json) so the CPU arm can convert steps/s to partitions/s."""
@@ -246,7 +257,8 @@ def main():
     ctx.plan_next_map(t, out)               # warm-up of the e2e path
     barrier()
     e2e_s = []
-    for _ in range(args.steps):
+    e2e_steps = args.steps
+    for _ in range(e2e_steps):
         t0 = time.perf_counter()
         ctx.plan_next_map(t, out)
         e2e_s.append(time.perf_counter() - t0)
@@ -289,7 +301,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_assign_pass", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(steps_per_plan * args.steps / max(1, pass_launches)),
                          "peak_source": peak_src, "bytes_per_findBestNodes_step": bytes_per_step,
                          "steps_per_launch": steps_per_plan * args.steps / max(1, pass_launches),
                          "t_step_ns": 1e9 * pass_s / (steps_per_plan * args.steps),
