@@ -1,0 +1,490 @@
+// blance_b200/csrc/assign_pass_seq.cuh — the assign pass for rebalances: a sequencer
+// warp decides the "sticky" steps alone and wakes the whole CTA only when it must.
+//
+// Same chain as assign_pass.cuh (assignStateToPartitions + findBestNodes,
+// plan.go:98-303), same results.  The observation: in a rebalance most steps re-elect the
+// partition's current nodes.  Every node score is bounded below by its "base" key — the
+// same formula (plan.go:634-689) with nodeToNodeCounts = 0 and no stickiness; all its
+// operations are monotone — and base keys only change when a count changes.  So:
+//
+//   * the CTA keeps the BL_GLIST smallest base keys of the live nodes in shared memory
+//     (glist) and a shared-memory mirror of the per-node score inputs;
+//   * the SEQUENCER warp (the service warp of the lock-step kernel) walks the steps.  For
+//     a step whose partition holds exactly k clean current nodes it computes their k exact
+//     scores from the mirror (lane q = current node q), finds the smallest cached base key
+//     among the nodes the partition could still take, and if the worst current node beats
+//     it, the reference's sort would put exactly the current nodes first: the step is
+//     decided by ONE warp with no barrier and no arg-min round (counts do not change, so
+//     the cache stays valid; only nodeToNodeCounts is bumped);
+//   * any other step is handed to the compute warps through two named barriers: they run
+//     the full evaluation (the code of the lock-step kernel), update their registers, the
+//     mirror and the base keys, and report the outcome; a count change drops the cache, which
+//     is rebuilt (BL_GLIST arg-min rounds) after BL_CALM_MIN quiet steps.
+//
+// The host picks this kernel per pass when the state has no hierarchy rules, k <= BL_FAST_K
+// and at least a quarter of the rows are eligible (k_pick_mode); otherwise the lock-step
+// kernel runs.
+#pragma once
+
+#include "pass_common.cuh"
+
+namespace blance_dev {
+
+#define BL_GLIST 8         // cached smallest base keys
+#define BL_FAST_K 4        // the sticky decision handles constraints up to this
+#define BL_CALM_MIN 3      // rebuild the cache only after this many steps without a count change
+#define SEQ_RING 128       // step-record ring of the sequencer kernel (records)
+#define SEQ_AHEAD 32       // records are requested (cp.async) at least this many steps ahead
+
+enum : int32_t { SEQ_CMD_EXIT = -1, SEQ_CMD_REBUILD = -2 };
+enum : int { BAR_GO = 1, BAR_DONE = 2, BAR_ROUND = 3 };
+enum : uint32_t { NF_VALID = 1, NF_BOOST = 2 };
+
+struct SeqSmem {
+  uint4 xchg[2][32];
+  alignas(16) int32_t ring[SEQ_RING][BL_REC_MAX];
+  double qtab[BL_QTAB];
+  alignas(16) int32_t slot_bit[BL_SLP_MAX];
+  uint4 glist[BL_GLIST];
+  int32_t cmd;
+  int32_t res_n, res_same;
+  int32_t res_chosen[BL_K_MAX];
+  int32_t g_len, g_complete;
+};
+
+// per-node mirror in dynamic shared memory: cd, ff, wd, wy (doubles) and a flag byte
+__device__ __forceinline__ size_t seq_dyn_smem_bytes(int N) { return (size_t)N * 33 + 16; }
+
+// CTA-wide arg-min over the compute warps only (named barrier BAR_ROUND, TC threads)
+__device__ __forceinline__ Best seq_argmin(Best mine, uint32_t xchg, int& xbuf, int cw, int TC, int warp, int lane) {
+  const Best w = warp_argmin(mine);
+  const uint32_t base = xchg + (uint32_t)xbuf * 512u;
+  if (lane == 0) sts128(base + (uint32_t)warp * 16u, w.hi, w.lo, w.pos, 0u);
+  bar_sync(BAR_ROUND, TC);
+  int4 e = make_int4(-1, -1, -1, 0);
+  if (lane < cw) e = lds128(base + (uint32_t)lane * 16u);
+  xbuf ^= 1;
+  return warp_argmin(Best{(uint32_t)e.x, (uint32_t)e.y, (uint32_t)e.z});
+}
+
+// exact key from explicit inputs (plan.go:634-689); flags: NF_BOOST => wd holds the (negative) weight
+__device__ __forceinline__ unsigned long long key_from(double cd, double ff, double wd, double wy, bool boost, bool has_nw,
+                                                       int32_t q, double cur, uint32_t qtab_a, double Pd, double Py) {
+  double qv = lds64f(qtab_a + ((uint32_t)q < BL_QTAB ? (uint32_t)q : 0u) * 8u);            // plan.go:641-642
+  if ((uint32_t)q >= BL_QTAB) qv = q_over_p_slow(q, Pd, Py);
+  const double base = __dadd_rn(__dadd_rn(cd, qv), ff);                                    // plan.go:672-673
+  double r = base;
+  if (has_nw && !boost) r = div_exact(r, wd, wy);                                          // plan.go:679 (identity for weight 1 / none)
+  if (boost) {                                                                             // plan.go:680-681, control_test.go:19-26
+    double b = -wd;
+    if (b < cur) b = cur;
+    r = __dadd_rn(base, b);
+  }
+  r = __dsub_rn(r, cur);                                                                   // plan.go:686
+  r = __dadd_rn(r, 0.0);                                                                   // -0.0 -> +0.0
+  return score_key(r);
+}
+
+// blockDim.x = TC + 32 (TC compute threads, a power of two) ; dynamic smem = seq_dyn_smem_bytes(N)
+template <int NPT, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s) {
+  DInst& D = pool.insts[blockIdx.x];
+  if (!D.active || s >= D.S || D.pass_mode != 1) return;
+  const int k = D.state_constraints[s];
+  if (k <= 0) return;
+
+  __shared__ SeqSmem sm;
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int NT = blockDim.x, TC = NT - 32, cw = TC >> 5;
+  const int logTC = 31 - __clz(TC);
+  const bool is_seq = warp == cw;
+  const int N = D.N, S = D.S, SL = D.SL, SLP = D.SLP;
+  const int n_assign = D.n_assign;
+  const int lo_s = D.state_slot_off[s];
+  const int Pn = D.P;
+  const double Pd = Pn > 0 ? (double)Pn : 1.0;
+  const double Py = __ddiv_rn(1.0, Pd);
+  const bool has_nw = D.has_node_weights != 0;
+
+  uint32_t higher_states = 0;              // bit s2: priority[s2] < priority[s]  (plan.go:146-152)
+  for (int s2 = 0; s2 < S; ++s2)
+    if (D.state_priority[s2] < D.state_priority[s]) higher_states |= 1u << s2;
+
+  const int REC = SLP + BL_REC_HDR;
+  const int32_t* stream = pool.stream + D.stream_off;
+  int32_t* ostream = pool.ostream + D.stream_off;
+  int32_t* counts = pool.counts + D.counts_off;
+  int32_t* n2n = pool.n2n + D.n2n_off;
+  const int32_t* extra = (D.use_rest ? pool.extra_rest : pool.extra_first) + D.node_off;
+
+  double* nd_cd = reinterpret_cast<double*>(dyn_smem);
+  double* nd_ff = nd_cd + N;
+  double* nd_wd = nd_ff + N;
+  double* nd_wy = nd_wd + N;
+  uint8_t* nd_flag = reinterpret_cast<uint8_t*>(nd_wy + N);
+
+  const uint32_t sm_a = (uint32_t)__cvta_generic_to_shared(&sm);
+  const uint32_t ring_a = sm_a + (uint32_t)offsetof(SeqSmem, ring);
+  const uint32_t xchg_a = sm_a + (uint32_t)offsetof(SeqSmem, xchg);
+  const uint32_t qtab_a = sm_a + (uint32_t)offsetof(SeqSmem, qtab);
+  const uint32_t sbit_a = sm_a + (uint32_t)offsetof(SeqSmem, slot_bit);
+  const uint32_t glist_a = sm_a + (uint32_t)offsetof(SeqSmem, glist);
+
+  // ---- pass constants ---------------------------------------------------------------------
+  for (int i = tid; i < SLP; i += NT) {
+    int st = 0;
+    while (st + 1 < S && i >= D.state_slot_off[st + 1]) ++st;
+    sm.slot_bit[i] = (i < SL) ? (1 << st) : 0;
+  }
+  for (int i = tid; i < BL_QTAB; i += NT) sm.qtab[i] = Pn > 0 ? __ddiv_rn((double)i, Pd) : 0.0;
+  if (tid == 0) { sm.cmd = 0; sm.g_len = 0; sm.g_complete = 0; sm.res_n = 0; sm.res_same = 0; }
+
+  // ---- per-node state: registers of the owner + shared mirror ----------------------------------
+  double cd[NPT], ff[NPT], wd[NPT], wy[NPT];
+  int32_t tot[NPT];
+  uint32_t valid_bits = 0, boost_bits = 0;
+#pragma unroll
+  for (int j = 0; j < NPT; ++j) {
+    const int n = tid + (j << logTC);
+    cd[j] = 0.0; ff[j] = 0.0; wd[j] = 1.0; wy[j] = 1.0; tot[j] = 0;
+    if (!is_seq && n < N) {
+      int t = extra[n];
+      for (int s2 = 0; s2 < S; ++s2) t += counts[s2 * N + n];
+      tot[j] = t;
+      cd[j] = (double)counts[s * N + n];
+      if (!pool.node_removed[D.nodeid_off + n]) valid_bits |= 1u << j;
+      if (has_nw && pool.node_has_weight[D.node_off + n]) {
+        const int w = pool.node_weight[D.node_off + n];
+        if (w > 1) { wd[j] = (double)w; wy[j] = __ddiv_rn(1.0, wd[j]); }          // plan.go:678-679
+        else if (w < 0 && D.booster == BLANCE_BOOSTER_CBGT_MAX) { boost_bits |= 1u << j; wd[j] = (double)w; }
+      }                                                                            // w == 0 / no booster: untouched
+      if (Pn > 0) ff[j] = div_exact(__dmul_rn(0.001, (double)t), Pd, Py);          // plan.go:650
+      nd_cd[n] = cd[j]; nd_ff[n] = ff[j]; nd_wd[n] = wd[j]; nd_wy[n] = wy[j];
+      nd_flag[n] = (uint8_t)((((valid_bits >> j) & 1u) ? NF_VALID : 0u) | (((boost_bits >> j) & 1u) ? NF_BOOST : 0u));
+    }
+  }
+  __syncthreads();   // constants, qtab (needed by the base keys) and the mirror are in place
+
+  unsigned long long Lk[NPT];               // base keys: n2n = 0, not current
+#pragma unroll
+  for (int j = 0; j < NPT; ++j)
+    Lk[j] = key_from(cd[j], ff[j], wd[j], wy[j], (boost_bits >> j) & 1u, has_nw, 0, 0.0, qtab_a, Pd, Py);
+  int xbuf = 0;
+
+  if (!is_seq) {
+    // =========================== compute warps: serve commands ====================================
+    for (;;) {
+      bar_sync(BAR_GO, NT);
+      const int32_t cmd = *(volatile int32_t*)&sm.cmd;
+      if (cmd == SEQ_CMD_EXIT) break;
+      if (cmd == SEQ_CMD_REBUILD) {
+        // BL_GLIST smallest (base key, position) over the live nodes, by repeated arg-min
+        uint32_t listed = 0;
+        int len = 0, complete = 0;
+        for (int r = 0; r < BL_GLIST; ++r) {
+          unsigned long long bk = ~0ull;
+          uint32_t bpos = 0xFFFFFFFFu;
+#pragma unroll
+          for (int j = 0; j < NPT; ++j)
+            if (((valid_bits & ~listed) >> j) & 1u)
+              if (bpos == 0xFFFFFFFFu || Lk[j] < bk) { bk = Lk[j]; bpos = (uint32_t)(tid + (j << logTC)); }
+          const Best b = seq_argmin(Best{(uint32_t)(bk >> 32), (uint32_t)bk, bpos}, xchg_a, xbuf, cw, TC, warp, lane);
+          if (b.pos == 0xFFFFFFFFu) { complete = 1; break; }
+          if (tid == 0) sts128(glist_a + (uint32_t)r * 16u, b.hi, b.lo, b.pos, 0u);
+          if ((b.pos & (uint32_t)(TC - 1)) == (uint32_t)tid) listed |= 1u << (b.pos >> logTC);
+          ++len;
+        }
+        if (tid == 0) { sm.g_len = len; sm.g_complete = complete; }
+        bar_sync(BAR_DONE, NT);
+        continue;
+      }
+      // ---- full evaluation of step `cmd` (the lock-step kernel's step) -------------------------------
+      const int i = cmd;
+      const uint32_t reca = ring_a + (uint32_t)(i % SEQ_RING) * (BL_REC_MAX * 4u);
+      const int4 hdr = lds128(reca + (uint32_t)SLP * 4u);               // meta, w_p, top, partition
+      const int32_t w_p = hdr.y, top = hdr.z;
+      const double stick = lds64f(reca + (uint32_t)SLP * 4u + 16u);
+      const int n_cur = lds32(reca + (uint32_t)(SLP + 6) * 4u);
+      const bool row_clean = lds32(reca + (uint32_t)(SLP + 7) * 4u) != 0;
+      int32_t qn[NPT];
+#pragma unroll
+      for (int j = 0; j < NPT; ++j) {
+        const int n = tid + (j << logTC);
+        qn[j] = (Pn > 0 && n < N) ? __ldcg(n2n + (size_t)top * N + n) : 0;
+      }
+      constexpr int MW = (NPT + 3) / 4;
+      uint32_t mw[MW];
+#pragma unroll
+      for (int w = 0; w < MW; ++w) mw[w] = 0;
+      for (int c = 0; c < (SLP >> 2); ++c) {
+        const int4 v = lds128(reca + (uint32_t)c * 16u), bb = lds128(sbit_a + (uint32_t)c * 16u);
+        const int32_t xs[4] = {v.x, v.y, v.z, v.w};
+        const int32_t bs[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int32_t x = xs[u];
+          const int jj = x >> logTC;
+          const uint32_t val = ((x & (TC - 1)) == tid) ? ((uint32_t)bs[u] << ((jj & 3) * 8)) : 0u;
+#pragma unroll
+          for (int w = 0; w < MW; ++w) mw[w] |= ((jj >> 2) == w) ? val : 0u;
+        }
+      }
+      uint32_t memb[NPT];
+      unsigned long long key[NPT];
+      uint32_t cand_bits = 0;
+#pragma unroll
+      for (int j = 0; j < NPT; ++j) {
+        memb[j] = (mw[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
+        const bool cand = ((valid_bits >> j) & 1u) && !(memb[j] & higher_states);   // plan.go:142-156
+        const double cur = ((memb[j] >> s) & 1u) ? stick : 0.0;                    // plan.go:654-662
+        const unsigned long long kk = key_from(cd[j], ff[j], wd[j], wy[j], (boost_bits >> j) & 1u, has_nw, qn[j], cur, qtab_a, Pd, Py);
+        key[j] = cand ? kk : ~0ull;
+        cand_bits |= (cand ? 1u : 0u) << j;
+      }
+      int n_chosen = 0;
+      uint32_t taken_bits = 0;
+      bool same = row_clean;
+      while (n_chosen < k) {                                // the flat (score, position) order
+        unsigned long long bk = ~0ull;
+        uint32_t bpos = 0xFFFFFFFFu;
+#pragma unroll
+        for (int j = 0; j < NPT; ++j)
+          if ((((cand_bits & ~taken_bits) >> j) & 1u) && (bpos == 0xFFFFFFFFu || key[j] < bk)) { bk = key[j]; bpos = (uint32_t)(tid + (j << logTC)); }
+        const uint32_t best = seq_argmin(Best{(uint32_t)(bk >> 32), (uint32_t)bk, bpos}, xchg_a, xbuf, cw, TC, warp, lane).pos;
+        if (best == 0xFFFFFFFFu) break;
+        if (tid == 0) sm.res_chosen[n_chosen] = (int32_t)best;
+        ++n_chosen;
+        if ((best & (uint32_t)(TC - 1)) == (uint32_t)tid) taken_bits |= 1u << (best >> logTC);
+        bool hit = false;
+        for (int q = 0; q < n_cur; ++q) hit = hit || ((uint32_t)lds32(reca + (uint32_t)(lo_s + q) * 4u) == best);
+        same = same && hit;
+      }
+      same = same && (n_chosen == n_cur);
+      if (tid == 0) { sm.res_n = n_chosen; sm.res_same = same ? 1 : 0; }
+      // ---- apply (plan.go:238-245, 290-301) on the owners' registers and the mirror --------------------
+      uint32_t touched = taken_bits;
+#pragma unroll
+      for (int w = 0; w < MW; ++w) touched |= mw[w];
+      if (touched)
+#pragma unroll
+      for (int j = 0; j < NPT; ++j) {
+        const bool is_cur = (memb[j] >> s) & 1u, tk = (taken_bits >> j) & 1u;
+        const int n = tid + (j << logTC);
+        if ((is_cur || tk) && n < N) {
+          int32_t t = tot[j];
+          uint32_t dec = memb[j];
+          const double wpd = (double)w_p;
+          if ((dec >> s) & 1u) { cd[j] = __dsub_rn(cd[j], wpd); t -= w_p; dec &= ~(1u << s); }
+          while (dec) {
+            const int s2 = __ffs(dec) - 1;
+            dec &= dec - 1;
+            atomicSub(&counts[s2 * N + n], w_p);
+            t -= w_p;
+          }
+          if (tk) {
+            cd[j] = __dadd_rn(cd[j], wpd);
+            t += w_p;
+            atomicAdd(&n2n[(size_t)top * N + n], 1);
+          }
+          if (t != tot[j]) {
+            tot[j] = t;
+            if (Pn > 0) ff[j] = div_exact(__dmul_rn(0.001, (double)t), Pd, Py);
+          }
+          nd_cd[n] = cd[j]; nd_ff[n] = ff[j];
+          Lk[j] = key_from(cd[j], ff[j], wd[j], wy[j], (boost_bits >> j) & 1u, has_nw, 0, 0.0, qtab_a, Pd, Py);
+        }
+      }
+      bar_sync(BAR_DONE, NT);
+    }
+    // ---- write the per-node counts of this state back ------------------------------------------------
+#pragma unroll
+    for (int j = 0; j < NPT; ++j) {
+      const int n = tid + (j << logTC);
+      if (n < N) counts[s * N + n] = __double2int_rn(cd[j]);
+    }
+    return;
+  }
+
+  // ================================ sequencer warp ====================================================
+  // A sticky step changes no count, so consecutive sticky steps depend on each other only through
+  // nodeToNodeCounts[top][node] (+1 per earlier step with the same top that kept the same node).  The
+  // warp therefore evaluates a WINDOW of 32/k consecutive steps at once - k lanes per step, lane q of a
+  // step = its q-th current node - assuming every earlier step of the window is sticky too (the extra
+  // n2n increments are counted with match.any); the window is then committed up to the first step that
+  // is not sticky, which goes to the compute warps, and the next window starts right after it.
+  // SIMD across STEPS instead of across nodes: one warp pass (one FP64 latency chain) decides up to 32
+  // steps.  (Rows have SLP <= 8 here: k_pick_mode.)
+  const int WS = 32 / k;                        // steps per window
+  const int wstep = lane / k, wq = lane - wstep * k, gb = wstep * k;
+  const bool wlane = wstep < WS;
+
+  // records stream into the ring with cp.async; `loaded` = first record not yet requested
+  int loaded = 0;
+  auto request_records = [&](int upto) {       // request records [loaded, min(upto, n_assign)) as one group
+    const int hi = upto < n_assign ? upto : n_assign;
+    const int words = (hi - loaded) * REC;
+    for (int w = lane; w < words; w += 32) {
+      const int step = loaded + w / REC, word = w - (w / REC) * REC;
+      const uint32_t dst = ring_a + ((uint32_t)(step % SEQ_RING) * BL_REC_MAX + (uint32_t)word) * 4u;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(stream + (size_t)step * REC + word) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (hi > loaded) loaded = hi;
+  };
+  request_records(2 * SEQ_AHEAD);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+
+  const uint32_t blk_mask = higher_states | (1u << s);
+  uint32_t slot_blocked = 0;                  // bit sl: a node in slot sl cannot be taken from the cached list
+  for (int sl = 0; sl < SL && sl < 8; ++sl)
+    if ((uint32_t)lds32(sbit_a + (uint32_t)sl * 4u) & blk_mask) slot_blocked |= 1u << sl;
+
+  int g_len = 0, g_complete = 0, calm = BL_CALM_MIN;
+  long long n_fast = 0;
+#ifdef BLANCE_PASS_TIMING
+  long long t_win = 0, n_win = 0, t_slow = 0, n_slow = 0, t_reb = 0, n_reb = 0;
+#endif
+
+  int i = 0;
+  while (i < n_assign) {
+#ifdef BLANCE_PASS_TIMING
+    long long t0 = clock64();
+#endif
+    // keep the ring >= 2*SEQ_AHEAD records ahead.  Invariant: loaded >= i + SEQ_AHEAD (a window is at most
+    // SEQ_AHEAD = 32 steps), so the group requested here never holds a record of the current window and
+    // may stay in flight; once nothing is left to request, everything must have landed.
+    if (loaded < n_assign && loaded < i + 2 * SEQ_AHEAD) {
+      request_records(i + 3 * SEQ_AHEAD);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+
+    // ---- my step of the window, my current node ---------------------------------------------------------
+    const int j = i + wstep;
+    const bool live = wlane && j < n_assign;
+    const uint32_t reca = ring_a + (uint32_t)((live ? j : i) % SEQ_RING) * (BL_REC_MAX * 4u);
+    const int4 r0 = lds128(reca);                                            // slots 0..3
+    const int4 r1 = SLP > 4 ? lds128(reca + 16u) : make_int4(-1, -1, -1, -1);   // slots 4..7
+    const int32_t top = lds32(reca + (uint32_t)(SLP + 2) * 4u);
+    const double stick = lds64f(reca + (uint32_t)SLP * 4u + 16u);
+    const int n_cur = lds32(reca + (uint32_t)(SLP + 6) * 4u);
+    const bool row_clean = lds32(reca + (uint32_t)(SLP + 7) * 4u) != 0;
+    const int32_t rowv[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+
+    // step i itself decides whether the cache has to be rebuilt first
+    const bool first_eligible = __shfl_sync(0xFFFFFFFFu, (int)(row_clean && n_cur == k), 0) != 0;
+    if (first_eligible && g_len == 0 && calm >= BL_CALM_MIN) {
+      if (lane == 0) *(volatile int32_t*)&sm.cmd = SEQ_CMD_REBUILD;
+      bar_sync(BAR_GO, NT);
+      bar_sync(BAR_DONE, NT);
+      g_len = *(volatile int32_t*)&sm.g_len;
+      g_complete = *(volatile int32_t*)&sm.g_complete;
+#ifdef BLANCE_PASS_TIMING
+      { long long t1 = clock64(); t_reb += t1 - t0; t0 = t1; ++n_reb; }
+#endif
+    }
+
+    int n_acc = 0;                              // leading sticky steps of this window
+    if (first_eligible && g_len > 0) {
+      const bool eligible = live && row_clean && n_cur == k;
+      int32_t c = -1;
+#pragma unroll
+      for (int sl = 0; sl < 8; ++sl) c = (sl == lo_s + wq) ? rowv[sl] : c;
+      if (!eligible) c = -1;
+      const int cc = c < 0 ? 0 : c;            // row_clean: 0 <= c < N
+      const double m_cd = nd_cd[cc], m_ff = nd_ff[cc], m_wd = nd_wd[cc], m_wy = nd_wy[cc];
+      const uint32_t fl = nd_flag[cc];
+      int32_t q = (eligible && Pn > 0) ? __ldcg(n2n + (size_t)top * N + cc) : 0;
+      // + the increments of the earlier steps of this window that share my (top, node)
+      const unsigned long long mk = eligible ? (((unsigned long long)(uint32_t)top << 32) | (uint32_t)c)
+                                             : (0xFFFFFFFF00000000ull | (uint32_t)lane);
+      const uint32_t same = __match_any_sync(0xFFFFFFFFu, mk);
+      q += __popc(same & ((1u << lane) - 1u));
+      unsigned long long mykey = ~0ull;
+      if (eligible) mykey = key_from(m_cd, m_ff, m_wd, m_wy, (fl & NF_BOOST) != 0, has_nw, q, stick, qtab_a, Pd, Py);
+      const bool ok_self = eligible && (fl & NF_VALID) != 0;
+      bool okl = true;                          // every current node of my step is a live candidate
+      // the k (key, node) pairs of my step: worst key of the step, my rank inside it
+      unsigned long long mxk = mykey;
+      int32_t mxp = c;
+      int rank = 0;
+      for (int t = 0; t < k; ++t) {
+        const unsigned long long ok_ = __shfl_sync(0xFFFFFFFFu, mykey, gb + t);
+        const int32_t oc = __shfl_sync(0xFFFFFFFFu, c, gb + t);
+        const bool okt = __shfl_sync(0xFFFFFFFFu, (int)ok_self, gb + t) != 0;
+        okl = okl && okt;
+        if (t != wq) {
+          if (ok_ < mykey || (ok_ == mykey && oc < c)) ++rank;
+          if (ok_ > mxk || (ok_ == mxk && oc > mxp)) { mxk = ok_; mxp = oc; }
+        }
+      }
+      // smallest cached base key among the nodes this row does not block
+      bool accept = false;
+      if (okl) {
+        bool found = false;
+        for (int g = 0; g < g_len && !found; ++g) {
+          const int4 e = lds128(glist_a + (uint32_t)g * 16u);
+          bool blocked = false;
+#pragma unroll
+          for (int sl = 0; sl < 8; ++sl) blocked = blocked || (((slot_blocked >> sl) & 1u) && rowv[sl] == e.z);
+          if (!blocked) {
+            found = true;
+            const unsigned long long gk = ((unsigned long long)(uint32_t)e.x << 32) | (uint32_t)e.y;
+            accept = mxk < gk || (mxk == gk && (uint32_t)mxp < (uint32_t)e.z);
+          }
+        }
+        if (!found) accept = g_complete != 0;   // every other live node is ineligible for this partition
+      }
+      // commit the leading run of sticky steps
+      const uint32_t rej = __ballot_sync(0xFFFFFFFFu, wlane && !accept);
+      const int first_rej_lane = rej ? (__ffs(rej) - 1) : 32;
+      n_acc = first_rej_lane / k;
+      if (n_acc > WS) n_acc = WS;
+      if (wlane && wstep < n_acc) {
+        atomicAdd(&n2n[(size_t)top * N + c], 1);                   // plan.go:238-245
+        int32_t* orec = ostream + (size_t)j * REC;
+        orec[rank] = c;                                            // ordered by (score, position)
+        if (wq == 0) orec[k] = k;
+      }
+      __syncwarp();                            // the REDs above are ordered before the next window's loads
+      n_fast += n_acc;
+      calm = calm + n_acc < (1 << 30) ? calm + n_acc : (1 << 30);
+      i += n_acc;
+#ifdef BLANCE_PASS_TIMING
+      { long long t1 = clock64(); t_win += t1 - t0; t0 = t1; ++n_win; }
+#endif
+      if (n_acc == WS || i >= n_assign) continue;                  // whole window sticky
+    }
+    // ---- step i is not sticky (or there is no cache): full evaluation by the compute warps ---------------
+    if (lane == 0) *(volatile int32_t*)&sm.cmd = i;
+    bar_sync(BAR_GO, NT);
+    bar_sync(BAR_DONE, NT);
+    {
+      const int n_chosen = *(volatile int32_t*)&sm.res_n;
+      int32_t* orec = ostream + (size_t)i * REC;
+      if (lane < k) orec[lane] = lane < n_chosen ? *(volatile int32_t*)&sm.res_chosen[lane] : BLANCE_NO_NODE;
+      if (lane == 0) orec[k] = n_chosen;
+      if (*(volatile int32_t*)&sm.res_same) { if (calm < (1 << 30)) ++calm; }
+      else { calm = 0; g_len = 0; }
+    }
+    ++i;
+#ifdef BLANCE_PASS_TIMING
+    { long long t1 = clock64(); t_slow += t1 - t0; ++n_slow; }
+#endif
+  }
+#ifdef BLANCE_PASS_TIMING
+  if (lane == 0 && blockIdx.x == 0)
+    printf("seq pass s=%d steps %d: sticky %lld in %lld windows (%.0f cyc/window, %.1f steps/window); full %lld (%.0f cyc each); rebuilds %lld (%.0f cyc each)\n",
+           s, n_assign, n_fast, n_win, n_win ? (double)t_win / n_win : 0.0, n_win ? (double)n_fast / n_win : 0.0, n_slow,
+           n_slow ? (double)t_slow / n_slow : 0.0, n_reb, n_reb ? (double)t_reb / n_reb : 0.0);
+#endif
+  if (lane == 0) *(volatile int32_t*)&sm.cmd = SEQ_CMD_EXIT;
+  bar_sync(BAR_GO, NT);
+  if (lane == 0) { D.steps += n_assign; D.fast_steps += n_fast; }
+}
+
+}  // namespace blance_dev

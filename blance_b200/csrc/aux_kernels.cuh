@@ -158,7 +158,7 @@ __global__ void k_build_keys(DPool pool, int s, long long n_parts_total) {
 
 // ---- step stream of a pass: records in the sorted order, so the sequential kernel reads linearly -----
 // record i of an instance (SLP + 8 words), pre-decoded so the chain does no per-step decoding:
-//   row[SLP] | meta, w_p, top, partition | stickiness (double), 2 spare words
+//   row[SLP] | meta, w_p, top, partition | stickiness (double), n_cur, row_clean
 // w_p = partition weight (plan.go:269-275), stickiness per plan.go:104-115, top = first node of the
 // top-priority state or NU for "" (plan.go:134-138).
 __global__ void k_gather_stream(DPool pool, int s, long long n_parts_total) {
@@ -190,9 +190,39 @@ __global__ void k_gather_stream(DPool pool, int s, long long n_parts_total) {
     const long long sb = __double_as_longlong(stick);
     dst[D.SLP + 4] = (int32_t)(sb & 0xFFFFFFFFll);
     dst[D.SLP + 5] = (int32_t)(sb >> 32);
-    dst[D.SLP + 6] = 0;
-    dst[D.SLP + 7] = 0;
+    // the current list of state s: its length, and whether it is "clean" (nodes distinct, inside
+    // nodesAll, and listed under no other state of this row) - the sticky fast path needs both
+    const int lo = D.state_slot_off[s], hi = D.state_slot_off[s + 1];
+    int n_cur = 0;
+    bool clean = true;
+    for (int a = lo; a < hi && row[a] != BLANCE_NO_NODE; ++a) {
+      ++n_cur;
+      if (row[a] >= D.N) clean = false;
+      for (int b = 0; b < D.SL; ++b)
+        if (b != a && row[b] == row[a]) clean = false;
+    }
+    dst[D.SLP + 6] = n_cur;
+    dst[D.SLP + 7] = clean ? 1 : 0;
+    if (clean && n_cur == D.state_constraints[s]) atomicAdd(&pool.insts[pool.part_inst[g]].n_elig, 1);
   }
+}
+
+// Which kernel runs the pass of state s for each instance (one thread per instance): the sequencer
+// kernel pays off when many rows can be decided by the sticky test; it needs k <= 4, no hierarchy
+// rules for the state, and a node mirror that fits in shared memory.
+__global__ void k_pick_mode(DPool pool, int s, int n_inst, int seq_allowed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_inst) return;
+  DInst& D = pool.insts[i];
+  int mode = 0;
+  if (D.active && s < D.S && D.state_constraints[s] > 0) {
+    const bool rules = D.has_hier_rules && D.rule_off[s + 1] > D.rule_off[s];
+    if (seq_allowed && !rules && D.state_constraints[s] <= 4 && D.N <= 4096 && D.SLP <= 8 && D.n_assign >= 64 &&
+        4ll * D.n_elig >= (long long)D.n_assign)
+      mode = 1;
+  }
+  D.pass_mode = mode;
+  D.n_elig = 0;
 }
 
 // After the pass: rebuild every partition's row from the step's outcome (plan.go:290-301), in

@@ -15,6 +15,7 @@
 #include <cub/device/device_segmented_radix_sort.cuh>
 
 #include "assign_pass.cuh"
+#include "assign_pass_seq.cuh"
 #include "aux_kernels.cuh"
 #include "blance_b200.h"
 #include "device_types.cuh"
@@ -412,6 +413,20 @@ static void launch_pass(const DPool& P, int n_inst, int T, int s, bool hier, cud
   else k_assign_pass<NPT, false, MAXT><<<n_inst, T, 0, st>>>(P, s);
 }
 
+// the sequencer variant; CTAs whose instance picked the other kernel exit at once
+template <int NPT, int MAXT>
+static cudaError_t launch_pass_seq(const DPool& P, int n_inst, int T, int s, int max_n, cudaStream_t st) {
+  const size_t dyn = (size_t)max_n * 33 + 16;
+  static size_t configured = 0;
+  if (dyn > configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_assign_pass_seq<NPT, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess) return e;
+    configured = dyn;
+  }
+  k_assign_pass_seq<NPT, MAXT><<<n_inst, T, dyn, st>>>(P, s);
+  return cudaSuccess;
+}
+
 static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 // Compute threads per CTA (TC, a power of two; the kernel adds one service warp) and nodes per
@@ -482,6 +497,7 @@ static int run(blance_ctx* ctx, blance_plan* pl) {
         CK(cub::DeviceSegmentedRadixSort::SortPairs(ctx->cub_tmp, tmp, P.keys_alt, P.keys, P.order_alt, P.order, (int)pl->PT,
                                                     n, pl->d_seg_off, pl->d_seg_off + 1, 0, 64, st));
       k_gather_stream<<<grid, blk, 0, st>>>(P, s, pl->PT);
+      k_pick_mode<<<(n + 127) / 128, 128, 0, st>>>(P, s, n, (npt <= 8 && !getenv("BLANCE_NO_SEQ")) ? 1 : 0);
       CK(cudaMemsetAsync(P.n2n, 0, sizeof(int32_t) * (size_t)(pl->N2T + 1), st));     // plan.go:266
       cudaEvent_t e0 = get_event(ctx, n_ev), e1 = get_event(ctx, n_ev + 1);
       if (e0 && e1 && n_ev < 256) CK(cudaEventRecord(e0, st));
@@ -490,6 +506,13 @@ static int run(blance_ctx* ctx, blance_plan* pl) {
       else if (npt == 4) launch_pass<4, 544>(P, n, T + 32, s, any_hier, st);
       else if (npt == 8) launch_pass<8, 544>(P, n, T + 32, s, any_hier, st);
       else launch_pass<16, 544>(P, n, T + 32, s, any_hier, st);
+      cudaError_t se = cudaSuccess;
+      if (npt == 1) se = (launch_pass_seq<1, 544>)(P, n, T + 32, s, pl->max_N, st);
+      else if (npt == 2) se = (launch_pass_seq<2, 544>)(P, n, T + 32, s, pl->max_N, st);
+      else if (npt == 4) se = (launch_pass_seq<4, 544>)(P, n, T + 32, s, pl->max_N, st);
+      else if (npt == 8) se = (launch_pass_seq<8, 544>)(P, n, T + 32, s, pl->max_N, st);
+      CK(se);
+      ctx->launches += 2;   // k_pick_mode + the sequencer kernel
       CK(cudaGetLastError());
       if (e0 && e1 && n_ev < 256) { CK(cudaEventRecord(e1, st)); n_ev += 2; }
       pl->pass_launches++;

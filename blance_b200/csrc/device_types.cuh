@@ -24,7 +24,7 @@
 #define BL_K_MAX 16       // constraints per state
 #define BL_SLP_MAX 32     // padded slots per row
 #define BL_PICK_MAX 32    // hierarchy picks per step (rules x constraints)
-#define BL_RING 4         // step-record ring depth in shared memory
+#define BL_RING 8         // step-record ring depth in shared memory (records i .. i+3 live, i+4 in flight)
 
 enum : uint8_t { PF_IN_PREV = 1, PF_IN_ASSIGN = 2, PF_HAS_WEIGHT = 4 };
 
@@ -44,8 +44,11 @@ struct DInst {
   int32_t add_is_nil;      // nodesToAdd == nil (plan.go:554)
   int32_t use_rest;        // extra_tot_rest instead of extra_tot_first
   int32_t active, converged, iters_run, mismatch;
+  int32_t pass_mode;       // kernel of the current pass: 0 lock-step (assign_pass.cuh), 1 sequencer (assign_pass_seq.cuh)
+  int32_t n_elig;          // rows of the current pass that hold exactly k clean current nodes (k_gather_stream)
   int32_t pad_;
   long long steps;
+  long long fast_steps;    // steps decided by the sequencer alone
 };
 
 struct DPool {

@@ -1,0 +1,86 @@
+// blance_b200/csrc/pass_common.cuh — helpers shared by the two assign-pass kernels
+// (assign_pass.cuh: all warps in lock step; assign_pass_seq.cuh: sequencer warp + on-demand CTA).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdio>
+
+#include "blance_b200.h"
+#include "device_types.cuh"
+
+namespace blance_dev {
+
+#define BL_QTAB 64
+#define BL_REC_HDR 8        // record = row[SLP] | meta, w_p, top, partition | stick (2 words), 2 spare
+#define BL_REC_MAX (BL_SLP_MAX + BL_REC_HDR)
+
+struct Best { uint32_t hi, lo, pos; };
+
+// Explicit .shared::cta accesses with 32-bit addresses for the hot loop (the generic-pointer
+// path makes the compiler rebuild the shared window base from SR_CgaCtaId inside the loop).
+__device__ __forceinline__ int4 lds128(uint32_t a) {
+  int4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ double lds64f(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int32_t lds32(uint32_t a) {
+  int32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" :: "r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t a, int32_t x) {
+  asm volatile("st.shared.b32 [%0], %1;" :: "r"(a), "r"(x) : "memory");
+}
+
+
+// order-preserving map double -> uint64 (total order == numeric order for non-NaN)
+__device__ __forceinline__ unsigned long long score_key(double r) {
+  const long long b = __double_as_longlong(r);
+  return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ull));
+}
+
+// lexicographic min of (hi, lo, pos) over the warp; non-participants pass all-ones
+__device__ __forceinline__ Best warp_argmin(Best v) {
+  const unsigned full = 0xFFFFFFFFu;
+  const uint32_t mhi = __reduce_min_sync(full, v.hi);
+  const uint32_t lo2 = (v.hi == mhi) ? v.lo : 0xFFFFFFFFu;
+  const uint32_t mlo = __reduce_min_sync(full, lo2);
+  const uint32_t p2 = (lo2 == mlo && v.hi == mhi) ? v.pos : 0xFFFFFFFFu;
+  const uint32_t mpos = __reduce_min_sync(full, p2);
+  return Best{mhi, mlo, mpos};
+}
+
+
+// a / b, correctly rounded, from y = RN(1/b): q0 = RN(a*y); two rounds of
+// q += RN(a - b*q) * y.  After the first round q is within (1/2 + eps) ulp of a/b
+// (a faithful rounding), so the second round returns RN(a/b) (Markstein's theorem;
+// b is a nonzero integer-valued double, a is far from the overflow/underflow range).
+// b == 1 (y == 1) returns a unchanged.
+__device__ __forceinline__ double div_exact(double a, double b, double y) {
+  double q = __dmul_rn(a, y);
+  double e = __fma_rn(-b, q, a);
+  q = __fma_rn(e, y, q);
+  e = __fma_rn(-b, q, a);
+  return __fma_rn(e, y, q);
+}
+
+// rare path: n2n count beyond the j/P table
+__device__ __noinline__ double q_over_p_slow(int32_t q, double Pd, double Py);
+
+
+__device__ __noinline__ double q_over_p_slow(int32_t q, double Pd, double Py) { return div_exact((double)q, Pd, Py); }
+
+// named barriers (id 0 is __syncthreads)
+__device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory"); }
+
+}  // namespace blance_dev
