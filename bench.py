@@ -300,7 +300,7 @@ def main():
                     "ms_per_step": 1e3 * e2e_total / args.steps, "result_equals_resident_run": same},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_assign_pass", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_assign_pass_seq + k_assign_pass (the two assign-pass kernels; per pass one of them runs)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(steps_per_plan * args.steps / max(1, pass_launches)),
                          "peak_source": peak_src, "bytes_per_findBestNodes_step": bytes_per_step,
                          "steps_per_launch": steps_per_plan * args.steps / max(1, pass_launches),

@@ -342,6 +342,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s) 
     if ((uint32_t)lds32(sbit_a + (uint32_t)sl * 4u) & blk_mask) slot_blocked |= 1u << sl;
 
   int g_len = 0, g_complete = 0, calm = BL_CALM_MIN;
+  // How many quiet steps to wait before rebuilding the cache: none while rebuilds pay off (the
+  // cache served at least 8 sticky steps before it was dropped), up to BL_CALM_MIN otherwise.
+  int need_calm = 0, served = 0;
   long long n_fast = 0;
 #ifdef BLANCE_PASS_TIMING
   long long t_win = 0, n_win = 0, t_slow = 0, n_slow = 0, t_reb = 0, n_reb = 0;
@@ -377,7 +380,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s) 
 
     // step i itself decides whether the cache has to be rebuilt first
     const bool first_eligible = __shfl_sync(0xFFFFFFFFu, (int)(row_clean && n_cur == k), 0) != 0;
-    if (first_eligible && g_len == 0 && calm >= BL_CALM_MIN) {
+    if (first_eligible && g_len == 0 && calm >= need_calm) {
+      served = 0;
       if (lane == 0) *(volatile int32_t*)&sm.cmd = SEQ_CMD_REBUILD;
       bar_sync(BAR_GO, NT);
       bar_sync(BAR_DONE, NT);
@@ -398,7 +402,18 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s) 
       const int cc = c < 0 ? 0 : c;            // row_clean: 0 <= c < N
       const double m_cd = nd_cd[cc], m_ff = nd_ff[cc], m_wd = nd_wd[cc], m_wy = nd_wy[cc];
       const uint32_t fl = nd_flag[cc];
-      int32_t q = (eligible && Pn > 0) ? __ldcg(n2n + (size_t)top * N + cc) : 0;
+      int32_t q = (eligible && Pn > 0) ? __ldcg(n2n + (size_t)top * N + cc) : 0;    // L2 latency, overlapped below
+      // smallest cached base key among the nodes this row does not block (independent of q)
+      bool g_found = false;
+      unsigned long long gk = 0;
+      uint32_t gp = 0;
+      for (int g = 0; g < g_len && !g_found; ++g) {
+        const int4 e = lds128(glist_a + (uint32_t)g * 16u);
+        bool blocked = false;
+#pragma unroll
+        for (int sl = 0; sl < 8; ++sl) blocked = blocked || (((slot_blocked >> sl) & 1u) && rowv[sl] == e.z);
+        if (!blocked) { g_found = true; gk = ((unsigned long long)(uint32_t)e.x << 32) | (uint32_t)e.y; gp = (uint32_t)e.z; }
+      }
       // + the increments of the earlier steps of this window that share my (top, node)
       const unsigned long long mk = eligible ? (((unsigned long long)(uint32_t)top << 32) | (uint32_t)c)
                                              : (0xFFFFFFFF00000000ull | (uint32_t)lane);
@@ -422,23 +437,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s) 
           if (ok_ > mxk || (ok_ == mxk && oc > mxp)) { mxk = ok_; mxp = oc; }
         }
       }
-      // smallest cached base key among the nodes this row does not block
       bool accept = false;
-      if (okl) {
-        bool found = false;
-        for (int g = 0; g < g_len && !found; ++g) {
-          const int4 e = lds128(glist_a + (uint32_t)g * 16u);
-          bool blocked = false;
-#pragma unroll
-          for (int sl = 0; sl < 8; ++sl) blocked = blocked || (((slot_blocked >> sl) & 1u) && rowv[sl] == e.z);
-          if (!blocked) {
-            found = true;
-            const unsigned long long gk = ((unsigned long long)(uint32_t)e.x << 32) | (uint32_t)e.y;
-            accept = mxk < gk || (mxk == gk && (uint32_t)mxp < (uint32_t)e.z);
-          }
-        }
-        if (!found) accept = g_complete != 0;   // every other live node is ineligible for this partition
-      }
+      if (okl) accept = g_found ? (mxk < gk || (mxk == gk && (uint32_t)mxp < gp))
+                                : (g_complete != 0);   // every other live node is ineligible for this partition
       // commit the leading run of sticky steps
       const uint32_t rej = __ballot_sync(0xFFFFFFFFu, wlane && !accept);
       const int first_rej_lane = rej ? (__ffs(rej) - 1) : 32;
@@ -452,6 +453,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s) 
       }
       __syncwarp();                            // the REDs above are ordered before the next window's loads
       n_fast += n_acc;
+      served += n_acc;
       calm = calm + n_acc < (1 << 30) ? calm + n_acc : (1 << 30);
       i += n_acc;
 #ifdef BLANCE_PASS_TIMING
@@ -469,7 +471,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s) 
       if (lane < k) orec[lane] = lane < n_chosen ? *(volatile int32_t*)&sm.res_chosen[lane] : BLANCE_NO_NODE;
       if (lane == 0) orec[k] = n_chosen;
       if (*(volatile int32_t*)&sm.res_same) { if (calm < (1 << 30)) ++calm; }
-      else { calm = 0; g_len = 0; }
+      else {
+        if (g_len > 0) need_calm = served >= 8 ? 0 : (need_calm < BL_CALM_MIN ? need_calm + 1 : BL_CALM_MIN);
+        calm = 0; g_len = 0;
+      }
     }
     ++i;
 #ifdef BLANCE_PASS_TIMING
