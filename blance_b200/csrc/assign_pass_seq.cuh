@@ -166,6 +166,12 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s) 
   }
   __syncthreads();   // constants, qtab (needed by the base keys) and the mirror are in place
 
+  // A row blocks at most (its k current nodes + the nodes it holds in higher-priority states) entries of
+  // the cached list, so that many + 2 entries are enough to always find an unblocked one.
+  int glist_want = k + 2;
+  for (int s2 = 0; s2 < S; ++s2)
+    if ((higher_states >> s2) & 1u) glist_want += D.state_slot_off[s2 + 1] - D.state_slot_off[s2];
+  if (glist_want > BL_GLIST) glist_want = BL_GLIST;
   unsigned long long Lk[NPT];               // base keys: n2n = 0, not current
 #pragma unroll
   for (int j = 0; j < NPT; ++j)
@@ -182,7 +188,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s) 
         // BL_GLIST smallest (base key, position) over the live nodes, by repeated arg-min
         uint32_t listed = 0;
         int len = 0, complete = 0;
-        for (int r = 0; r < BL_GLIST; ++r) {
+        for (int r = 0; r < glist_want; ++r) {
           unsigned long long bk = ~0ull;
           uint32_t bpos = 0xFFFFFFFFu;
 #pragma unroll
