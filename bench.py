@@ -269,6 +269,13 @@ def main():
     e2e_total = float(te[0])
     same = bool(np.array_equal(out.next_rows, res.next_rows))
 
+    # ---- CalcPartitionMoves over the whole map (prev -> next), through the C ABI with host buffers -----
+    ctx.calc_partition_moves(t.state_slot_off, t.prev_rows, out.next_rows, False)
+    t0 = time.perf_counter()
+    mv = ctx.calc_partition_moves(t.state_slot_off, t.prev_rows, out.next_rows, False)
+    moves_s = time.perf_counter() - t0
+    moves_ops = int(mv[3].sum())
+
     if rank == 0:
         P, N = t.n_parts, t.n_nodes
         value = world * P * args.steps / (total_ms_max / 1e3)
@@ -298,6 +305,9 @@ def main():
                        "timing": "CUDA events on the library stream, max over ranks"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * e2e_total / args.steps, "result_equals_resident_run": same},
+            "calc_partition_moves": {"partitions_per_s": P / moves_s, "ms": 1e3 * moves_s, "ops": moves_ops,
+                                     "note": "moves.go:41-119 for all partitions in one launch, prevMap -> nextMap, host buffers "
+                                             "(H2D of both maps and D2H of the op lists inside the timed call)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_assign_pass_seq + k_assign_pass (the two assign-pass kernels; per pass one of them runs)", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -217,7 +217,7 @@ __global__ void k_pick_mode(DPool pool, int s, int n_inst, int seq_allowed) {
   int mode = 0;
   if (D.active && s < D.S && D.state_constraints[s] > 0) {
     const bool rules = D.has_hier_rules && D.rule_off[s + 1] > D.rule_off[s];
-    if (seq_allowed && !rules && D.state_constraints[s] <= 4 && D.N <= 4096 && D.SLP <= 8 && D.n_assign >= 64 &&
+    if (seq_allowed && D.engine == BLANCE_ENGINE_AUTO && !rules && D.state_constraints[s] <= 4 && D.N <= 4096 && D.SLP <= 8 && D.n_assign >= 64 &&
         4ll * D.n_elig >= (long long)D.n_assign)
       mode = 1;
   }

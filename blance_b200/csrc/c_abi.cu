@@ -32,6 +32,13 @@ struct blance_ctx {
   std::mutex mu;
   void* cub_tmp = nullptr;
   size_t cub_tmp_bytes = 0;
+  // one device arena and one pinned staging buffer are kept between calls (grow-only), so a
+  // steady stream of PlanNextMapEx calls does not pay cudaMalloc / cudaMallocHost every time
+  void* spare_arena = nullptr;
+  size_t spare_arena_bytes = 0;
+  void* spare_stage = nullptr;
+  size_t spare_stage_bytes = 0;
+  size_t seq_dyn_configured[4] = {0, 0, 0, 0};   // opted-in dynamic shared memory of k_assign_pass_seq<1|2|4|8>
   std::vector<cudaEvent_t> events;   // pool for pass timing
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   int* d_any_active = nullptr;
@@ -103,6 +110,8 @@ extern "C" void blance_ctx_destroy(blance_ctx* ctx) {
   for (auto ev : ctx->events) cudaEventDestroy(ev);
   for (auto ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   if (ctx->cub_tmp) cudaFree(ctx->cub_tmp);
+  if (ctx->spare_arena) cudaFree(ctx->spare_arena);
+  if (ctx->spare_stage) cudaFreeHost(ctx->spare_stage);
   if (ctx->d_any_active) cudaFree(ctx->d_any_active);
   if (ctx->h_any_active) cudaFreeHost(ctx->h_any_active);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -180,15 +189,30 @@ static int validate(blance_ctx* ctx, const blance_plan_in* in, int idx) {
       if ((in->rule_off[s + 1] - in->rule_off[s]) * std::max(0, in->state_constraints[s]) > BL_PICK_MAX)
         return bad("rules x constraints > 32 for one state", BLANCE_ERR_UNSUPPORTED);
   }
+  if (in->engine != BLANCE_ENGINE_AUTO && in->engine != BLANCE_ENGINE_LOCKSTEP) return bad("unknown engine", BLANCE_ERR_UNSUPPORTED);
   if (in->booster_kind != BLANCE_BOOSTER_NONE && in->booster_kind != BLANCE_BOOSTER_CBGT_MAX)
     return bad("unknown booster_kind", BLANCE_ERR_UNSUPPORTED);
   return BLANCE_OK;
 }
 
-static void plan_release(blance_plan* pl) {
+static void plan_release(blance_plan* pl, blance_ctx* ctx = nullptr) {
   if (!pl) return;
-  if (pl->arena) cudaFree(pl->arena);
-  if (pl->h_stage) cudaFreeHost(pl->h_stage);
+  if (pl->arena) {
+    if (ctx && pl->arena_bytes > ctx->spare_arena_bytes) {          // keep the larger one for the next call
+      if (ctx->spare_arena) cudaFree(ctx->spare_arena);
+      ctx->spare_arena = pl->arena; ctx->spare_arena_bytes = pl->arena_bytes;
+    } else {
+      cudaFree(pl->arena);
+    }
+  }
+  if (pl->h_stage) {
+    if (ctx && pl->h_stage_bytes > ctx->spare_stage_bytes) {
+      if (ctx->spare_stage) cudaFreeHost(ctx->spare_stage);
+      ctx->spare_stage = pl->h_stage; ctx->spare_stage_bytes = pl->h_stage_bytes;
+    } else {
+      cudaFreeHost(pl->h_stage);
+    }
+  }
   delete pl;
 }
 
@@ -224,7 +248,7 @@ static int upload(blance_ctx* ctx, int n, const blance_plan_in* ins, blance_plan
     D.n_rules = in.has_hier_rules ? in.n_rules : 0;
     D.top_state = in.top_state; D.booster = in.booster_kind;
     D.has_part_weights = in.has_part_weights; D.has_node_weights = in.has_node_weights;
-    D.has_hier_rules = in.has_hier_rules; D.max_iters = in.max_iters;
+    D.has_hier_rules = in.has_hier_rules; D.max_iters = in.max_iters; D.engine = in.engine;
     for (int s = 0; s < in.n_states; ++s) {
       D.state_priority[s] = in.state_priority[s];
       D.state_constraints[s] = in.state_constraints[s];
@@ -285,7 +309,13 @@ static int upload(blance_ctx* ctx, int n, const blance_plan_in* ins, blance_plan
 #undef SL_
   size_t total = 0;
   for (auto& s : slices) total += align_up(s.bytes, 256);
-  cudaError_t e = cudaMalloc(&pl->arena, total);
+  cudaError_t e = cudaSuccess;
+  if (ctx->spare_arena && ctx->spare_arena_bytes >= total) {
+    pl->arena = ctx->spare_arena; total = ctx->spare_arena_bytes;
+    ctx->spare_arena = nullptr; ctx->spare_arena_bytes = 0;
+  } else {
+    e = cudaMalloc(&pl->arena, total);
+  }
   if (e != cudaSuccess) {
     plan_release(pl);
     return fail(ctx, BLANCE_ERR_NOMEM, std::string("cudaMalloc of the plan arena failed: ") + cudaGetErrorString(e));
@@ -303,12 +333,18 @@ static int upload(blance_ctx* ctx, int n, const blance_plan_in* ins, blance_plan
   const size_t stage_bytes = align_up(sizeof(int32_t) * RRT, 256) * 2 + align_up(RST, 256) * 2 + align_up(PT, 256) +
                              align_up(sizeof(int32_t) * PT, 256) * 3 + align_up(NUT, 256) * 2 +
                              align_up(sizeof(int32_t) * NT, 256) * 3 + align_up(NT, 256) + align_up(sizeof(uint32_t) * MT, 256);
-  e = cudaMallocHost(&pl->h_stage, stage_bytes);
+  size_t stage_have = stage_bytes;
+  if (ctx->spare_stage && ctx->spare_stage_bytes >= stage_bytes) {
+    pl->h_stage = ctx->spare_stage; stage_have = ctx->spare_stage_bytes;
+    ctx->spare_stage = nullptr; ctx->spare_stage_bytes = 0;
+  } else {
+    e = cudaMallocHost(&pl->h_stage, stage_bytes);
+  }
   if (e != cudaSuccess) {
     plan_release(pl);
     return fail(ctx, BLANCE_ERR_NOMEM, std::string("cudaMallocHost of the staging buffer failed: ") + cudaGetErrorString(e));
   }
-  pl->h_stage_bytes = stage_bytes;
+  pl->h_stage_bytes = stage_have;
   char* hp = (char*)pl->h_stage;
   auto carve = [&](size_t bytes) { char* r = hp; hp += align_up(bytes, 256); return r; };
   int32_t* h_cur = (int32_t*)carve(sizeof(int32_t) * RRT);
@@ -387,6 +423,8 @@ static int upload(blance_ctx* ctx, int n, const blance_plan_in* ins, blance_plan
   need = std::max(need, need2);
   if (need > ctx->cub_tmp_bytes) {
     if (ctx->cub_tmp) cudaFree(ctx->cub_tmp);
+  if (ctx->spare_arena) cudaFree(ctx->spare_arena);
+  if (ctx->spare_stage) cudaFreeHost(ctx->spare_stage);
     ctx->cub_tmp = nullptr; ctx->cub_tmp_bytes = 0;
     e = cudaMalloc(&ctx->cub_tmp, need);
     if (e != cudaSuccess) { plan_release(pl); return fail(ctx, BLANCE_ERR_NOMEM, "cudaMalloc of the sort scratch failed"); }
@@ -415,13 +453,12 @@ static void launch_pass(const DPool& P, int n_inst, int T, int s, bool hier, cud
 
 // the sequencer variant; CTAs whose instance picked the other kernel exit at once
 template <int NPT, int MAXT>
-static cudaError_t launch_pass_seq(const DPool& P, int n_inst, int T, int s, int max_n, cudaStream_t st) {
+static cudaError_t launch_pass_seq(size_t* configured, const DPool& P, int n_inst, int T, int s, int max_n, cudaStream_t st) {
   const size_t dyn = (size_t)max_n * 33 + 16;
-  static size_t configured = 0;
-  if (dyn > configured) {
+  if (dyn > *configured) {          // function attributes are per device: tracked in the context
     cudaError_t e = cudaFuncSetAttribute(k_assign_pass_seq<NPT, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return e;
-    configured = dyn;
+    *configured = dyn;
   }
   k_assign_pass_seq<NPT, MAXT><<<n_inst, T, dyn, st>>>(P, s);
   return cudaSuccess;
@@ -507,10 +544,10 @@ static int run(blance_ctx* ctx, blance_plan* pl) {
       else if (npt == 8) launch_pass<8, 544>(P, n, T + 32, s, any_hier, st);
       else launch_pass<16, 544>(P, n, T + 32, s, any_hier, st);
       cudaError_t se = cudaSuccess;
-      if (npt == 1) se = (launch_pass_seq<1, 544>)(P, n, T + 32, s, pl->max_N, st);
-      else if (npt == 2) se = (launch_pass_seq<2, 544>)(P, n, T + 32, s, pl->max_N, st);
-      else if (npt == 4) se = (launch_pass_seq<4, 544>)(P, n, T + 32, s, pl->max_N, st);
-      else if (npt == 8) se = (launch_pass_seq<8, 544>)(P, n, T + 32, s, pl->max_N, st);
+      if (npt == 1) se = (launch_pass_seq<1, 544>)(&ctx->seq_dyn_configured[0], P, n, T + 32, s, pl->max_N, st);
+      else if (npt == 2) se = (launch_pass_seq<2, 544>)(&ctx->seq_dyn_configured[1], P, n, T + 32, s, pl->max_N, st);
+      else if (npt == 4) se = (launch_pass_seq<4, 544>)(&ctx->seq_dyn_configured[2], P, n, T + 32, s, pl->max_N, st);
+      else if (npt == 8) se = (launch_pass_seq<8, 544>)(&ctx->seq_dyn_configured[3], P, n, T + 32, s, pl->max_N, st);
       CK(se);
       ctx->launches += 2;   // k_pick_mode + the sequencer kernel
       CK(cudaGetLastError());
@@ -614,7 +651,7 @@ extern "C" int blance_plan_timing(const blance_plan* plan, float* kernel_ms, flo
 
 extern "C" void blance_plan_free(blance_ctx* ctx, blance_plan* plan) {
   if (!plan) return;
-  if (ctx) { std::lock_guard<std::mutex> g(ctx->mu); cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); plan_release(plan); }
+  if (ctx) { std::lock_guard<std::mutex> g(ctx->mu); cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); plan_release(plan, ctx); }
   else plan_release(plan);
 }
 
@@ -636,7 +673,7 @@ static int plan_batch(blance_ctx* ctx, int32_t n, const blance_plan_in* in, blan
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]);
     for (int i = 0; i < n; ++i) out[i].device_ms = ms;
   }
-  plan_release(pl);
+  plan_release(pl, ctx);
   return st;
 }
 

@@ -56,7 +56,7 @@ struct PlanNextMapOptions {            // api.go:183-190
   // The package-level knobs of plan.go, which a C ABI cannot read from Go globals:
   int MaxIterationsPerPlan = 10;       // plan.go:21
   int NodeScoreBooster = BLANCE_BOOSTER_NONE;   // plan.go:693; enum blance_booster
-  int Engine = BLANCE_ENGINE_AUTO;     // enum blance_engine (not in the reference)
+  int Engine = BLANCE_ENGINE_AUTO;     // enum blance_engine (not in the reference; results do not depend on it)
 };
 
 using Warnings = std::unordered_map<std::string, Strs>;

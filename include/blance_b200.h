@@ -56,11 +56,12 @@ enum blance_status {
  * only booster in the reference tree is cbgt's (control_test.go:19-26). */
 enum blance_booster { BLANCE_BOOSTER_NONE = 0, BLANCE_BOOSTER_CBGT_MAX = 1 };
 
-/* Which engine runs the sequential greedy chain of one state pass. */
+/* Which kernel runs the sequential greedy chain of a state pass.  AUTO picks per
+ * pass: the sequencer kernel when many rows are sticky, the lock-step kernel otherwise.  Results are
+ * identical either way. */
 enum blance_engine {
   BLANCE_ENGINE_AUTO = 0,
-  BLANCE_ENGINE_EXACT_CTA = 1,    /* one CTA per instance, threads over nodes */
-  BLANCE_ENGINE_EXACT_WARP = 2    /* one warp per instance (n_nodes <= 1024), used by the batch path */
+  BLANCE_ENGINE_LOCKSTEP = 1      /* never use the sequencer kernel */
 };
 
 typedef struct blance_ctx blance_ctx;   /* owns the device, streams, scratch buffers */

@@ -110,14 +110,18 @@ def test_all_nodes_removed_gives_nil_lists(ctx):
 
 # ---- BASELINE.json configurations ---------------------------------------------------------------
 
-def two_stage(ctx, cfg, P=None):
+def two_stage(ctx, cfg, P=None, engine=0):
+    """fresh placement, then the configuration's rebalance; engine 0 = auto (the sequencer kernel takes the
+    sticky passes), 1 = lock-step kernel only.  Both must equal the oracle bit for bit."""
     fresh = synth.make_fresh(cfg, P=P)
+    fresh.engine = engine
     ref1 = oracle_tables(fresh)
     got1 = ctx.plan_next_map(fresh)
     assert_same(got1, ref1)
     if cfg == 1:
         return got1
     reb = synth.make_rebalance(cfg, None if cfg == 4 else got1.next_rows, P=P)
+    reb.engine = engine
     ref2 = oracle_tables(reb)
     got2 = ctx.plan_next_map(reb)
     assert_same(got2, ref2)
@@ -138,6 +142,29 @@ def test_cfg3_65536x256_three_states_zone_rack(ctx):
 
 def test_cfg4_weights_stickiness_reduced(ctx):
     two_stage(ctx, 4, P=32768)
+
+
+@pytest.mark.parametrize("cfg,P", [(2, None), (3, 8192), (4, 16384)])
+def test_lockstep_engine_only(ctx, cfg, P):
+    two_stage(ctx, cfg, P=P, engine=1)
+
+
+def test_sequencer_odd_shapes(ctx):
+    """k = 3 (10 steps per window), a 4th state with k = 0 and nodes that are not a power of two."""
+    t = synth.PlanTables(200, 3, 6000, [0, 1, 2], [1, 3, 0])
+    rng = np.random.default_rng(5)
+    rows = np.stack([rng.permutation(180)[:4] for _ in range(t.n_parts)]).astype(np.int32)
+    t.prev_rows[:] = rows
+    t.cur_rows[:] = rows
+    t.prev_shape[:, :2] = 2
+    t.cur_shape[:, :2] = 2
+    t.part_in_prev[:] = 1
+    t.node_removed[:5] = 1
+    t.node_added[180:] = 1
+    t.has_node_weights = 1
+    t.node_has_weight[:] = 1
+    t.node_weight[:] = rng.integers(1, 6, t.n_nodes)
+    assert_same(ctx.plan_next_map(t), oracle_tables(t))
 
 
 def test_cfg4_full_size_properties(ctx):
