@@ -24,6 +24,11 @@ using namespace blance_dev;
 
 static std::string g_create_error;
 
+// Opted-in dynamic shared memory of k_assign_pass_seq<1|2|4|8>, per device.  The attribute belongs to the
+// (function, device) pair, not to a blance_ctx, and must only ever be raised.
+static std::mutex g_seq_dyn_mu;
+static size_t g_seq_dyn[64][4];
+
 struct blance_ctx {
   int device = 0;
   int sm_count = 148;
@@ -32,13 +37,6 @@ struct blance_ctx {
   std::mutex mu;
   void* cub_tmp = nullptr;
   size_t cub_tmp_bytes = 0;
-  // one device arena and one pinned staging buffer are kept between calls (grow-only), so a
-  // steady stream of PlanNextMapEx calls does not pay cudaMalloc / cudaMallocHost every time
-  void* spare_arena = nullptr;
-  size_t spare_arena_bytes = 0;
-  void* spare_stage = nullptr;
-  size_t spare_stage_bytes = 0;
-  size_t seq_dyn_configured[4] = {0, 0, 0, 0};   // opted-in dynamic shared memory of k_assign_pass_seq<1|2|4|8>
   std::vector<cudaEvent_t> events;   // pool for pass timing
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   int* d_any_active = nullptr;
@@ -110,8 +108,6 @@ extern "C" void blance_ctx_destroy(blance_ctx* ctx) {
   for (auto ev : ctx->events) cudaEventDestroy(ev);
   for (auto ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   if (ctx->cub_tmp) cudaFree(ctx->cub_tmp);
-  if (ctx->spare_arena) cudaFree(ctx->spare_arena);
-  if (ctx->spare_stage) cudaFreeHost(ctx->spare_stage);
   if (ctx->d_any_active) cudaFree(ctx->d_any_active);
   if (ctx->h_any_active) cudaFreeHost(ctx->h_any_active);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -196,23 +192,10 @@ static int validate(blance_ctx* ctx, const blance_plan_in* in, int idx) {
 }
 
 static void plan_release(blance_plan* pl, blance_ctx* ctx = nullptr) {
+  (void)ctx;
   if (!pl) return;
-  if (pl->arena) {
-    if (ctx && pl->arena_bytes > ctx->spare_arena_bytes) {          // keep the larger one for the next call
-      if (ctx->spare_arena) cudaFree(ctx->spare_arena);
-      ctx->spare_arena = pl->arena; ctx->spare_arena_bytes = pl->arena_bytes;
-    } else {
-      cudaFree(pl->arena);
-    }
-  }
-  if (pl->h_stage) {
-    if (ctx && pl->h_stage_bytes > ctx->spare_stage_bytes) {
-      if (ctx->spare_stage) cudaFreeHost(ctx->spare_stage);
-      ctx->spare_stage = pl->h_stage; ctx->spare_stage_bytes = pl->h_stage_bytes;
-    } else {
-      cudaFreeHost(pl->h_stage);
-    }
-  }
+  if (pl->arena) cudaFree(pl->arena);
+  if (pl->h_stage) cudaFreeHost(pl->h_stage);
   delete pl;
 }
 
@@ -232,6 +215,10 @@ static int upload(blance_ctx* ctx, int n, const blance_plan_in* ins, blance_plan
     if (st != BLANCE_OK) return st;
   }
   CK(cudaSetDevice(ctx->device));
+  {
+    cudaError_t stale = cudaGetLastError();      // never let an earlier, unrelated error be blamed on this call
+    if (stale != cudaSuccess) return fail(ctx, BLANCE_ERR_CUDA, std::string("a previous CUDA call on this thread failed: ") + cudaGetErrorString(stale));
+  }
   blance_plan* pl = new blance_plan();
   pl->n_inst = n;
   pl->h_insts.resize(n);
@@ -309,13 +296,7 @@ static int upload(blance_ctx* ctx, int n, const blance_plan_in* ins, blance_plan
 #undef SL_
   size_t total = 0;
   for (auto& s : slices) total += align_up(s.bytes, 256);
-  cudaError_t e = cudaSuccess;
-  if (ctx->spare_arena && ctx->spare_arena_bytes >= total) {
-    pl->arena = ctx->spare_arena; total = ctx->spare_arena_bytes;
-    ctx->spare_arena = nullptr; ctx->spare_arena_bytes = 0;
-  } else {
-    e = cudaMalloc(&pl->arena, total);
-  }
+  cudaError_t e = cudaMalloc(&pl->arena, total);
   if (e != cudaSuccess) {
     plan_release(pl);
     return fail(ctx, BLANCE_ERR_NOMEM, std::string("cudaMalloc of the plan arena failed: ") + cudaGetErrorString(e));
@@ -333,18 +314,12 @@ static int upload(blance_ctx* ctx, int n, const blance_plan_in* ins, blance_plan
   const size_t stage_bytes = align_up(sizeof(int32_t) * RRT, 256) * 2 + align_up(RST, 256) * 2 + align_up(PT, 256) +
                              align_up(sizeof(int32_t) * PT, 256) * 3 + align_up(NUT, 256) * 2 +
                              align_up(sizeof(int32_t) * NT, 256) * 3 + align_up(NT, 256) + align_up(sizeof(uint32_t) * MT, 256);
-  size_t stage_have = stage_bytes;
-  if (ctx->spare_stage && ctx->spare_stage_bytes >= stage_bytes) {
-    pl->h_stage = ctx->spare_stage; stage_have = ctx->spare_stage_bytes;
-    ctx->spare_stage = nullptr; ctx->spare_stage_bytes = 0;
-  } else {
-    e = cudaMallocHost(&pl->h_stage, stage_bytes);
-  }
+  e = cudaMallocHost(&pl->h_stage, stage_bytes);
   if (e != cudaSuccess) {
     plan_release(pl);
     return fail(ctx, BLANCE_ERR_NOMEM, std::string("cudaMallocHost of the staging buffer failed: ") + cudaGetErrorString(e));
   }
-  pl->h_stage_bytes = stage_have;
+  pl->h_stage_bytes = stage_bytes;
   char* hp = (char*)pl->h_stage;
   auto carve = [&](size_t bytes) { char* r = hp; hp += align_up(bytes, 256); return r; };
   int32_t* h_cur = (int32_t*)carve(sizeof(int32_t) * RRT);
@@ -409,6 +384,7 @@ static int upload(blance_ctx* ctx, int n, const blance_plan_in* ins, blance_plan
                                                         pl->d_raw_rows_off, pl->d_raw_shape_off, pl->PT);
     ctx->launches++;
     e = cudaGetLastError();
+    if (e != cudaSuccess) { plan_release(pl); return fail(ctx, BLANCE_ERR_CUDA, std::string("k_unpack launch failed: ") + cudaGetErrorString(e)); }
     if (e == cudaSuccess) e = cudaMemcpyAsync(pl->rows_init, P.rows, sizeof(int32_t) * (size_t)pl->RT, cudaMemcpyDeviceToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(pl->prev_rows_init, P.prev_rows, sizeof(int32_t) * (size_t)pl->RT, cudaMemcpyDeviceToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(pl->pmeta_init, P.pmeta, sizeof(uint32_t) * (size_t)pl->PT, cudaMemcpyDeviceToDevice, st);
@@ -423,15 +399,13 @@ static int upload(blance_ctx* ctx, int n, const blance_plan_in* ins, blance_plan
   need = std::max(need, need2);
   if (need > ctx->cub_tmp_bytes) {
     if (ctx->cub_tmp) cudaFree(ctx->cub_tmp);
-  if (ctx->spare_arena) cudaFree(ctx->spare_arena);
-  if (ctx->spare_stage) cudaFreeHost(ctx->spare_stage);
     ctx->cub_tmp = nullptr; ctx->cub_tmp_bytes = 0;
     e = cudaMalloc(&ctx->cub_tmp, need);
     if (e != cudaSuccess) { plan_release(pl); return fail(ctx, BLANCE_ERR_NOMEM, "cudaMalloc of the sort scratch failed"); }
     ctx->cub_tmp_bytes = need;
   }
   e = cudaStreamSynchronize(st);
-  if (e != cudaSuccess) { plan_release(pl); return fail(ctx, BLANCE_ERR_CUDA, std::string("upload failed: ") + cudaGetErrorString(e)); }
+  if (e != cudaSuccess) { plan_release(pl); return fail(ctx, BLANCE_ERR_CUDA, std::string("upload sync failed: ") + cudaGetErrorString(e)); }
   *out_plan = pl;
   return BLANCE_OK;
 }
@@ -455,10 +429,13 @@ static void launch_pass(const DPool& P, int n_inst, int T, int s, bool hier, cud
 template <int NPT, int MAXT>
 static cudaError_t launch_pass_seq(size_t* configured, const DPool& P, int n_inst, int T, int s, int max_n, cudaStream_t st) {
   const size_t dyn = (size_t)max_n * 33 + 16;
-  if (dyn > *configured) {          // function attributes are per device: tracked in the context
-    cudaError_t e = cudaFuncSetAttribute(k_assign_pass_seq<NPT, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    if (e != cudaSuccess) return e;
-    *configured = dyn;
+  {
+    std::lock_guard<std::mutex> g(g_seq_dyn_mu);
+    if (dyn > *configured) {
+      cudaError_t e = cudaFuncSetAttribute(k_assign_pass_seq<NPT, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+      if (e != cudaSuccess) return e;
+      *configured = dyn;
+    }
   }
   k_assign_pass_seq<NPT, MAXT><<<n_inst, T, dyn, st>>>(P, s);
   return cudaSuccess;
@@ -544,11 +521,12 @@ static int run(blance_ctx* ctx, blance_plan* pl) {
       else if (npt == 8) launch_pass<8, 544>(P, n, T + 32, s, any_hier, st);
       else launch_pass<16, 544>(P, n, T + 32, s, any_hier, st);
       cudaError_t se = cudaSuccess;
-      if (npt == 1) se = (launch_pass_seq<1, 544>)(&ctx->seq_dyn_configured[0], P, n, T + 32, s, pl->max_N, st);
-      else if (npt == 2) se = (launch_pass_seq<2, 544>)(&ctx->seq_dyn_configured[1], P, n, T + 32, s, pl->max_N, st);
-      else if (npt == 4) se = (launch_pass_seq<4, 544>)(&ctx->seq_dyn_configured[2], P, n, T + 32, s, pl->max_N, st);
-      else if (npt == 8) se = (launch_pass_seq<8, 544>)(&ctx->seq_dyn_configured[3], P, n, T + 32, s, pl->max_N, st);
+      if (npt == 1) se = (launch_pass_seq<1, 544>)(&g_seq_dyn[ctx->device & 63][0], P, n, T + 32, s, pl->max_N, st);
+      else if (npt == 2) se = (launch_pass_seq<2, 544>)(&g_seq_dyn[ctx->device & 63][1], P, n, T + 32, s, pl->max_N, st);
+      else if (npt == 4) se = (launch_pass_seq<4, 544>)(&g_seq_dyn[ctx->device & 63][2], P, n, T + 32, s, pl->max_N, st);
+      else if (npt == 8) se = (launch_pass_seq<8, 544>)(&g_seq_dyn[ctx->device & 63][3], P, n, T + 32, s, pl->max_N, st);
       CK(se);
+      CK(cudaGetLastError());
       ctx->launches += 2;   // k_pick_mode + the sequencer kernel
       CK(cudaGetLastError());
       if (e0 && e1 && n_ev < 256) { CK(cudaEventRecord(e1, st)); n_ev += 2; }
