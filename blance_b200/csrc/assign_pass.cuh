@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass(DPool pool, int s) {
         r = __dadd_rn(base, b);
       }
       r = __dsub_rn(r, cur);                                                     // plan.go:686
-      r = __dadd_rn(r, 0.0);                                                     // -0.0 -> +0.0 (equal under Go's <)
+      // (r is never -0.0: counts convert to +0.0, x - x rounds to +0.0, and +0.0 / w = +0.0)
       key[j] = cand ? score_key(r) : ~0ull;
       cand_bits |= (cand ? 1u : 0u) << j;
     }

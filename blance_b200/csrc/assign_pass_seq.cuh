@@ -81,7 +81,7 @@ __device__ __forceinline__ unsigned long long key_from(double cd, double ff, dou
     r = __dadd_rn(base, b);
   }
   r = __dsub_rn(r, cur);                                                                   // plan.go:686
-  r = __dadd_rn(r, 0.0);                                                                   // -0.0 -> +0.0
+  // (r is never -0.0: counts convert to +0.0, x - x rounds to +0.0, and +0.0 / w = +0.0)
   return score_key(r);
 }
 

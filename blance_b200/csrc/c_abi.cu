@@ -310,7 +310,27 @@ static int upload(blance_ctx* ctx, int n, const blance_plan_in* ins, blance_plan
   P.node_removed = c_rm; P.node_added = c_ad; P.node_weight = c_nw; P.node_has_weight = c_hw;
   P.extra_first = c_ef; P.extra_rest = c_er; P.ie_mask = c_mask;
 
-  // ---- pinned staging: concatenate the batch in caller layout, then copy ------------------
+  // ---- host side of the copy.  A batch is concatenated in caller layout into one pinned staging buffer;
+  // a single instance is copied straight from the caller's arrays (no staging, no pinned allocation).
+  const bool direct = (n == 1);
+  const int32_t *h_cur = nullptr, *h_prev = nullptr, *h_pw = nullptr, *h_rank = nullptr, *h_inst = nullptr;
+  const int32_t *h_nw = nullptr, *h_ef = nullptr, *h_er = nullptr;
+  const uint8_t *h_csh = nullptr, *h_psh = nullptr, *h_flags = nullptr, *h_rm = nullptr, *h_ad = nullptr, *h_hw = nullptr;
+  const uint32_t* h_mask = nullptr;
+  std::vector<uint8_t> v_flags;
+  if (direct) {
+    const blance_plan_in& in = ins[0];
+    const DInst& D = pl->h_insts[0];
+    v_flags.resize((size_t)D.PU + 1);
+    for (int p = 0; p < D.PU; ++p)
+      v_flags[p] = (uint8_t)((in.part_in_prev[p] ? PF_IN_PREV : 0) | (in.part_in_assign[p] ? PF_IN_ASSIGN : 0) |
+                             (in.part_has_weight[p] ? PF_HAS_WEIGHT : 0));
+    h_cur = in.cur_rows; h_prev = in.prev_rows; h_csh = in.cur_shape; h_psh = in.prev_shape;
+    h_flags = v_flags.data(); h_pw = in.part_weight; h_rank = in.part_name_rank;     // h_inst stays NULL: all zero
+    h_rm = in.node_removed; h_ad = in.node_added;
+    if (in.has_node_weights) { h_nw = in.node_weight; h_hw = in.node_has_weight; }
+    h_ef = in.extra_tot_first; h_er = in.extra_tot_rest; h_mask = in.ie_mask;
+  } else {
   const size_t stage_bytes = align_up(sizeof(int32_t) * RRT, 256) * 2 + align_up(RST, 256) * 2 + align_up(PT, 256) +
                              align_up(sizeof(int32_t) * PT, 256) * 3 + align_up(NUT, 256) * 2 +
                              align_up(sizeof(int32_t) * NT, 256) * 3 + align_up(NT, 256) + align_up(sizeof(uint32_t) * MT, 256);
@@ -322,48 +342,52 @@ static int upload(blance_ctx* ctx, int n, const blance_plan_in* ins, blance_plan
   pl->h_stage_bytes = stage_bytes;
   char* hp = (char*)pl->h_stage;
   auto carve = [&](size_t bytes) { char* r = hp; hp += align_up(bytes, 256); return r; };
-  int32_t* h_cur = (int32_t*)carve(sizeof(int32_t) * RRT);
-  int32_t* h_prev = (int32_t*)carve(sizeof(int32_t) * RRT);
-  uint8_t* h_csh = (uint8_t*)carve(RST);
-  uint8_t* h_psh = (uint8_t*)carve(RST);
-  uint8_t* h_flags = (uint8_t*)carve(PT);
-  int32_t* h_pw = (int32_t*)carve(sizeof(int32_t) * PT);
-  int32_t* h_rank = (int32_t*)carve(sizeof(int32_t) * PT);
-  int32_t* h_inst = (int32_t*)carve(sizeof(int32_t) * PT);
-  uint8_t* h_rm = (uint8_t*)carve(NUT);
-  uint8_t* h_ad = (uint8_t*)carve(NUT);
-  int32_t* h_nw = (int32_t*)carve(sizeof(int32_t) * NT);
-  int32_t* h_ef = (int32_t*)carve(sizeof(int32_t) * NT);
-  int32_t* h_er = (int32_t*)carve(sizeof(int32_t) * NT);
-  uint8_t* h_hw = (uint8_t*)carve(NT);
-  uint32_t* h_mask = (uint32_t*)carve(sizeof(uint32_t) * MT);
+  int32_t* s_cur = (int32_t*)carve(sizeof(int32_t) * RRT);
+  int32_t* s_prev = (int32_t*)carve(sizeof(int32_t) * RRT);
+  uint8_t* s_csh = (uint8_t*)carve(RST);
+  uint8_t* s_psh = (uint8_t*)carve(RST);
+  uint8_t* s_flags = (uint8_t*)carve(PT);
+  int32_t* s_pw = (int32_t*)carve(sizeof(int32_t) * PT);
+  int32_t* s_rank = (int32_t*)carve(sizeof(int32_t) * PT);
+  int32_t* s_inst = (int32_t*)carve(sizeof(int32_t) * PT);
+  uint8_t* s_rm = (uint8_t*)carve(NUT);
+  uint8_t* s_ad = (uint8_t*)carve(NUT);
+  int32_t* s_nw = (int32_t*)carve(sizeof(int32_t) * NT);
+  int32_t* s_ef = (int32_t*)carve(sizeof(int32_t) * NT);
+  int32_t* s_er = (int32_t*)carve(sizeof(int32_t) * NT);
+  uint8_t* s_hw = (uint8_t*)carve(NT);
+  uint32_t* s_mask = (uint32_t*)carve(sizeof(uint32_t) * MT);
   for (int i = 0; i < n; ++i) {
     const blance_plan_in& in = ins[i];
     const DInst& D = pl->h_insts[i];
     const size_t rr = (size_t)D.PU * D.SL, rs = (size_t)D.PU * D.S;
-    if (rr) { std::memcpy(h_cur + pl->raw_rows_off[i], in.cur_rows, sizeof(int32_t) * rr);
-              std::memcpy(h_prev + pl->raw_rows_off[i], in.prev_rows, sizeof(int32_t) * rr); }
-    if (rs) { std::memcpy(h_csh + pl->raw_shape_off[i], in.cur_shape, rs); std::memcpy(h_psh + pl->raw_shape_off[i], in.prev_shape, rs); }
+    if (rr) { std::memcpy(s_cur + pl->raw_rows_off[i], in.cur_rows, sizeof(int32_t) * rr);
+              std::memcpy(s_prev + pl->raw_rows_off[i], in.prev_rows, sizeof(int32_t) * rr); }
+    if (rs) { std::memcpy(s_csh + pl->raw_shape_off[i], in.cur_shape, rs); std::memcpy(s_psh + pl->raw_shape_off[i], in.prev_shape, rs); }
     for (int p = 0; p < D.PU; ++p) {
       const size_t g = (size_t)D.part_off + p;
-      h_flags[g] = (uint8_t)((in.part_in_prev[p] ? PF_IN_PREV : 0) | (in.part_in_assign[p] ? PF_IN_ASSIGN : 0) |
+      s_flags[g] = (uint8_t)((in.part_in_prev[p] ? PF_IN_PREV : 0) | (in.part_in_assign[p] ? PF_IN_ASSIGN : 0) |
                              (in.part_has_weight[p] ? PF_HAS_WEIGHT : 0));
-      h_pw[g] = in.part_weight[p];
-      h_rank[g] = in.part_name_rank[p];
-      h_inst[g] = i;
+      s_pw[g] = in.part_weight[p];
+      s_rank[g] = in.part_name_rank[p];
+      s_inst[g] = i;
     }
-    if (D.NU) { std::memcpy(h_rm + D.nodeid_off, in.node_removed, D.NU); std::memcpy(h_ad + D.nodeid_off, in.node_added, D.NU); }
+    if (D.NU) { std::memcpy(s_rm + D.nodeid_off, in.node_removed, D.NU); std::memcpy(s_ad + D.nodeid_off, in.node_added, D.NU); }
     for (int q = 0; q < D.N; ++q) {
-      h_nw[D.node_off + q] = in.has_node_weights ? in.node_weight[q] : 0;
-      h_hw[D.node_off + q] = in.has_node_weights ? in.node_has_weight[q] : 0;
-      h_ef[D.node_off + q] = in.extra_tot_first ? in.extra_tot_first[q] : 0;
-      h_er[D.node_off + q] = in.extra_tot_rest ? in.extra_tot_rest[q] : 0;
+      s_nw[D.node_off + q] = in.has_node_weights ? in.node_weight[q] : 0;
+      s_hw[D.node_off + q] = in.has_node_weights ? in.node_has_weight[q] : 0;
+      s_ef[D.node_off + q] = in.extra_tot_first ? in.extra_tot_first[q] : 0;
+      s_er[D.node_off + q] = in.extra_tot_rest ? in.extra_tot_rest[q] : 0;
     }
     const size_t mw = (size_t)D.n_rules * (D.NU + 1) * D.HW;
-    if (mw) std::memcpy(h_mask + D.mask_off, in.ie_mask, sizeof(uint32_t) * mw);
+    if (mw) std::memcpy(s_mask + D.mask_off, in.ie_mask, sizeof(uint32_t) * mw);
+  }
+  h_cur = s_cur; h_prev = s_prev; h_csh = s_csh; h_psh = s_psh; h_flags = s_flags; h_pw = s_pw; h_rank = s_rank;
+  h_inst = s_inst; h_rm = s_rm; h_ad = s_ad; h_nw = s_nw; h_hw = s_hw; h_ef = s_ef; h_er = s_er; h_mask = s_mask;
   }
   cudaStream_t st = ctx->stream;
-#define H2D(dst, src, bytes) do { if ((bytes) > 0) { e = cudaMemcpyAsync((void*)(dst), (src), (bytes), cudaMemcpyHostToDevice, st); \
+#define H2D(dst, src, bytes) do { if ((bytes) > 0) { \
+    e = (src) ? cudaMemcpyAsync((void*)(dst), (src), (bytes), cudaMemcpyHostToDevice, st) : cudaMemsetAsync((void*)(dst), 0, (bytes), st); \
     if (e != cudaSuccess) { plan_release(pl); return fail(ctx, BLANCE_ERR_CUDA, std::string("H2D copy failed: ") + cudaGetErrorString(e)); } } } while (0)
   H2D(pl->raw_a, h_cur, sizeof(int32_t) * (size_t)pl->RRT); H2D(pl->raw_b, h_prev, sizeof(int32_t) * (size_t)pl->RRT);
   H2D(pl->rawsh_a, h_csh, (size_t)pl->RST); H2D(pl->rawsh_b, h_psh, (size_t)pl->RST);
@@ -568,18 +592,24 @@ static int fetch(blance_ctx* ctx, blance_plan* pl, blance_plan_out* outs) {
     CK(cudaGetLastError());
     ctx->launches++;
   }
-  // results land in the pinned staging buffer (its head is large enough: it held cur+prev rows)
-  char* hp = (char*)pl->h_stage;
-  int32_t* h_rows = (int32_t*)hp;
-  hp += align_up(sizeof(int32_t) * ((size_t)pl->RRT + 1), 256) * 2;
-  uint8_t* h_shape = (uint8_t*)hp;
-  hp += align_up((size_t)pl->RST + 1, 256);
-  uint8_t* h_warn = (uint8_t*)hp;
-  if (pl->RRT) CK(cudaMemcpyAsync(h_rows, pl->raw_a, sizeof(int32_t) * (size_t)pl->RRT, cudaMemcpyDeviceToHost, st));
-  if (pl->RST) {
-    CK(cudaMemcpyAsync(h_shape, pl->rawsh_a, (size_t)pl->RST, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h_warn, pl->rawsh_b, (size_t)pl->RST, cudaMemcpyDeviceToHost, st));
+  // a single instance is copied straight into the caller's buffers; a batch lands in the pinned staging
+  // buffer first (its head is large enough: it held cur+prev rows)
+  int32_t* h_rows = nullptr;
+  uint8_t *h_shape = nullptr, *h_warn = nullptr;
+  const bool direct = pl->h_stage == nullptr;
+  if (direct) {
+    h_rows = outs[0].next_rows; h_shape = outs[0].next_shape; h_warn = outs[0].warn;
+  } else {
+    char* hp = (char*)pl->h_stage;
+    h_rows = (int32_t*)hp;
+    hp += align_up(sizeof(int32_t) * ((size_t)pl->RRT + 1), 256) * 2;
+    h_shape = (uint8_t*)hp;
+    hp += align_up((size_t)pl->RST + 1, 256);
+    h_warn = (uint8_t*)hp;
   }
+  if (pl->RRT && h_rows) CK(cudaMemcpyAsync(h_rows, pl->raw_a, sizeof(int32_t) * (size_t)pl->RRT, cudaMemcpyDeviceToHost, st));
+  if (pl->RST && h_shape) CK(cudaMemcpyAsync(h_shape, pl->rawsh_a, (size_t)pl->RST, cudaMemcpyDeviceToHost, st));
+  if (pl->RST && h_warn) CK(cudaMemcpyAsync(h_warn, pl->rawsh_b, (size_t)pl->RST, cudaMemcpyDeviceToHost, st));
   std::vector<DInst> fin(n);
   CK(cudaMemcpyAsync(fin.data(), pl->pool.insts, sizeof(DInst) * (size_t)n, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
@@ -587,9 +617,11 @@ static int fetch(blance_ctx* ctx, blance_plan* pl, blance_plan_out* outs) {
     const DInst& D = pl->h_insts[i];
     blance_plan_out& o = outs[i];
     const size_t rr = (size_t)D.PU * D.SL, rs = (size_t)D.PU * D.S;
-    if (rr && o.next_rows) std::memcpy(o.next_rows, h_rows + pl->raw_rows_off[i], sizeof(int32_t) * rr);
-    if (rs && o.next_shape) std::memcpy(o.next_shape, h_shape + pl->raw_shape_off[i], rs);
-    if (rs && o.warn) std::memcpy(o.warn, h_warn + pl->raw_shape_off[i], rs);
+    if (!direct) {
+      if (rr && o.next_rows) std::memcpy(o.next_rows, h_rows + pl->raw_rows_off[i], sizeof(int32_t) * rr);
+      if (rs && o.next_shape) std::memcpy(o.next_shape, h_shape + pl->raw_shape_off[i], rs);
+      if (rs && o.warn) std::memcpy(o.warn, h_warn + pl->raw_shape_off[i], rs);
+    }
     o.iters_run = fin[i].iters_run;
     o.converged = fin[i].converged;
     o.steps = fin[i].steps;

@@ -61,16 +61,17 @@ __device__ __forceinline__ Best warp_argmin(Best v) {
 }
 
 
-// a / b, correctly rounded, from y = RN(1/b): q0 = RN(a*y); two rounds of
-// q += RN(a - b*q) * y.  After the first round q is within (1/2 + eps) ulp of a/b
-// (a faithful rounding), so the second round returns RN(a/b) (Markstein's theorem;
-// b is a nonzero integer-valued double, a is far from the overflow/underflow range).
-// b == 1 (y == 1) returns a unchanged.
+// a / b, correctly rounded, for an integer-valued divisor 1 <= b < 2^31, from y = RN(1/b):
+//   q0 = RN(a*y);  e = a - b*q0 (exact in one FMA);  q1 = RN(q0 + e*y)  ==  RN(a/b).
+// Why one correction is enough here: q0 = (a/b)(1+e1)(1+e2) with |e1|,|e2| <= 2^-53, so the residual
+// a - b*q0 has at most ~32 significant bits (b has <= 31, the cancellation removes the rest) and the FMA
+// returns it exactly; then q0 + e*y = a/b + (a/b - q0)*e1, i.e. a/b perturbed by at most |a/b| * 2^-105,
+// while a/b (b an integer < 2^31, a a double) is never closer than |a/b| * 2^-84 to a rounding boundary
+// and never exactly on one (that would need a 54-bit significand in a).  tests/test_division.py checks
+// the sequence against true division on 4e7 adversarial operands.  b == 1 (y == 1) returns a unchanged.
 __device__ __forceinline__ double div_exact(double a, double b, double y) {
-  double q = __dmul_rn(a, y);
-  double e = __fma_rn(-b, q, a);
-  q = __fma_rn(e, y, q);
-  e = __fma_rn(-b, q, a);
+  const double q = __dmul_rn(a, y);
+  const double e = __fma_rn(-b, q, a);
   return __fma_rn(e, y, q);
 }
 
