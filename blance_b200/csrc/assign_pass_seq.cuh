@@ -86,12 +86,14 @@ __device__ __forceinline__ unsigned long long key_from(double cd, double ff, dou
 }
 
 // blockDim.x = TC + 32 (TC compute threads, a power of two) ; dynamic smem = seq_dyn_smem_bytes(N)
-template <int NPT, int MAXT>
+// K = the state's constraints (1..BL_FAST_K): a template parameter so that the per-step lane groups,
+// the key exchange and the divisions by k are compile-time.
+template <int NPT, int K, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s) {
   DInst& D = pool.insts[blockIdx.x];
   if (!D.active || s >= D.S || D.pass_mode != 1) return;
-  const int k = D.state_constraints[s];
-  if (k <= 0) return;
+  constexpr int k = K;
+  if (D.state_constraints[s] != K) return;       // this instantiation serves the instances whose state has exactly K
 
   __shared__ SeqSmem sm;
   extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -321,7 +323,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s) 
   // is not sticky, which goes to the compute warps, and the next window starts right after it.
   // SIMD across STEPS instead of across nodes: one warp pass (one FP64 latency chain) decides up to 32
   // steps.  (Rows have SLP <= 8 here: k_pick_mode.)
-  const int WS = 32 / k;                        // steps per window
+  constexpr int WS = 32 / K;                    // steps per window
   const int wstep = lane / k, wq = lane - wstep * k, gb = wstep * k;
   const bool wlane = wstep < WS;
 
@@ -329,11 +331,11 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s) 
   int loaded = 0;
   auto request_records = [&](int upto) {       // request records [loaded, min(upto, n_assign)) as one group
     const int hi = upto < n_assign ? upto : n_assign;
-    const int words = (hi - loaded) * REC;
-    for (int w = lane; w < words; w += 32) {
-      const int step = loaded + w / REC, word = w - (w / REC) * REC;
-      const uint32_t dst = ring_a + ((uint32_t)(step % SEQ_RING) * BL_REC_MAX + (uint32_t)word) * 4u;
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(stream + (size_t)step * REC + word) : "memory");
+    for (int step = loaded; step < hi; ++step) {            // one record per trip: lane = word (REC <= 40)
+      const uint32_t dst = ring_a + (uint32_t)(step % SEQ_RING) * (BL_REC_MAX * 4u);
+      const int32_t* src = stream + (size_t)step * REC;
+      if (lane < REC) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst + (uint32_t)lane * 4u), "l"(src + lane) : "memory");
+      if (lane + 32 < REC) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst + (uint32_t)(lane + 32) * 4u), "l"(src + lane + 32) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     if (hi > loaded) loaded = hi;
@@ -433,7 +435,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s) 
       unsigned long long mxk = mykey;
       int32_t mxp = c;
       int rank = 0;
-      for (int t = 0; t < k; ++t) {
+#pragma unroll
+      for (int t = 0; t < K; ++t) {
         const unsigned long long ok_ = __shfl_sync(0xFFFFFFFFu, mykey, gb + t);
         const int32_t oc = __shfl_sync(0xFFFFFFFFu, c, gb + t);
         const bool okt = __shfl_sync(0xFFFFFFFFu, (int)ok_self, gb + t) != 0;

@@ -27,7 +27,7 @@ static std::string g_create_error;
 // Opted-in dynamic shared memory of k_assign_pass_seq<1|2|4|8>, per device.  The attribute belongs to the
 // (function, device) pair, not to a blance_ctx, and must only ever be raised.
 static std::mutex g_seq_dyn_mu;
-static size_t g_seq_dyn[64][4];
+static size_t g_seq_dyn[64][4][4];   // [device][NPT index][K - 1]
 
 struct blance_ctx {
   int device = 0;
@@ -449,20 +449,32 @@ static void launch_pass(const DPool& P, int n_inst, int T, int s, bool hier, cud
   else k_assign_pass<NPT, false, MAXT><<<n_inst, T, 0, st>>>(P, s);
 }
 
-// the sequencer variant; CTAs whose instance picked the other kernel exit at once
-template <int NPT, int MAXT>
-static cudaError_t launch_pass_seq(size_t* configured, const DPool& P, int n_inst, int T, int s, int max_n, cudaStream_t st) {
-  const size_t dyn = (size_t)max_n * 33 + 16;
+// the sequencer variant, one instantiation per constraint count K; CTAs whose instance picked the other
+// kernel (or has a different K for this state) exit at once
+template <int NPT, int K, int MAXT>
+static cudaError_t launch_pass_seq_k(size_t* configured, const DPool& P, int n_inst, int T, int s, size_t dyn, cudaStream_t st) {
   {
     std::lock_guard<std::mutex> g(g_seq_dyn_mu);
     if (dyn > *configured) {
-      cudaError_t e = cudaFuncSetAttribute(k_assign_pass_seq<NPT, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+      cudaError_t e = cudaFuncSetAttribute(k_assign_pass_seq<NPT, K, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
       if (e != cudaSuccess) return e;
       *configured = dyn;
     }
   }
-  k_assign_pass_seq<NPT, MAXT><<<n_inst, T, dyn, st>>>(P, s);
+  k_assign_pass_seq<NPT, K, MAXT><<<n_inst, T, dyn, st>>>(P, s);
   return cudaSuccess;
+}
+
+// kmask: bit K set when some instance of the batch has constraints == K for state s
+template <int NPT, int MAXT>
+static cudaError_t launch_pass_seq(size_t* configured, const DPool& P, int n_inst, int T, int s, int max_n, unsigned kmask, cudaStream_t st) {
+  const size_t dyn = (size_t)max_n * 33 + 16;
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess && (kmask & 2u)) e = launch_pass_seq_k<NPT, 1, MAXT>(configured + 0, P, n_inst, T, s, dyn, st);
+  if (e == cudaSuccess && (kmask & 4u)) e = launch_pass_seq_k<NPT, 2, MAXT>(configured + 1, P, n_inst, T, s, dyn, st);
+  if (e == cudaSuccess && (kmask & 8u)) e = launch_pass_seq_k<NPT, 3, MAXT>(configured + 2, P, n_inst, T, s, dyn, st);
+  if (e == cudaSuccess && (kmask & 16u)) e = launch_pass_seq_k<NPT, 4, MAXT>(configured + 3, P, n_inst, T, s, dyn, st);
+  return e;
 }
 
 static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
@@ -545,13 +557,15 @@ static int run(blance_ctx* ctx, blance_plan* pl) {
       else if (npt == 8) launch_pass<8, 544>(P, n, T + 32, s, any_hier, st);
       else launch_pass<16, 544>(P, n, T + 32, s, any_hier, st);
       cudaError_t se = cudaSuccess;
-      if (npt == 1) se = (launch_pass_seq<1, 544>)(&g_seq_dyn[ctx->device & 63][0], P, n, T + 32, s, pl->max_N, st);
-      else if (npt == 2) se = (launch_pass_seq<2, 544>)(&g_seq_dyn[ctx->device & 63][1], P, n, T + 32, s, pl->max_N, st);
-      else if (npt == 4) se = (launch_pass_seq<4, 544>)(&g_seq_dyn[ctx->device & 63][2], P, n, T + 32, s, pl->max_N, st);
-      else if (npt == 8) se = (launch_pass_seq<8, 544>)(&g_seq_dyn[ctx->device & 63][3], P, n, T + 32, s, pl->max_N, st);
+      unsigned kmask = 0;
+      for (int i = 0; i < n; ++i) { const int kk = pl->h_insts[i].S > s ? pl->h_insts[i].state_constraints[s] : 0; if (kk >= 1 && kk <= 4) kmask |= 1u << kk; }
+      if (npt == 1) se = (launch_pass_seq<1, 544>)(g_seq_dyn[ctx->device & 63][0], P, n, T + 32, s, pl->max_N, kmask, st);
+      else if (npt == 2) se = (launch_pass_seq<2, 544>)(g_seq_dyn[ctx->device & 63][1], P, n, T + 32, s, pl->max_N, kmask, st);
+      else if (npt == 4) se = (launch_pass_seq<4, 544>)(g_seq_dyn[ctx->device & 63][2], P, n, T + 32, s, pl->max_N, kmask, st);
+      else if (npt == 8) se = (launch_pass_seq<8, 544>)(g_seq_dyn[ctx->device & 63][3], P, n, T + 32, s, pl->max_N, kmask, st);
       CK(se);
       CK(cudaGetLastError());
-      ctx->launches += 2;   // k_pick_mode + the sequencer kernel
+      ctx->launches += 1 + (npt <= 8 ? __builtin_popcount(kmask) : 0);   // k_pick_mode + the sequencer kernel(s)
       CK(cudaGetLastError());
       if (e0 && e1 && n_ev < 256) { CK(cudaEventRecord(e1, st)); n_ev += 2; }
       pl->pass_launches++;
