@@ -95,6 +95,13 @@ extern "C" int blance_ctx_create(blance_ctx** out, int device_id) {
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
   for (auto& ev : ctx->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+  {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
+      unsigned long long keep = ~0ull;              // keep freed arenas cached in the pool between calls
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   if ((e = cudaMalloc(&ctx->d_any_active, sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMallocHost(&ctx->h_any_active, sizeof(int))) != cudaSuccess) return bail("cudaMallocHost", e);
   *out = ctx;
@@ -192,9 +199,11 @@ static int validate(blance_ctx* ctx, const blance_plan_in* in, int idx) {
 }
 
 static void plan_release(blance_plan* pl, blance_ctx* ctx = nullptr) {
-  (void)ctx;
   if (!pl) return;
-  if (pl->arena) cudaFree(pl->arena);
+  if (pl->arena) {
+    if (ctx) cudaFreeAsync(pl->arena, ctx->stream);     // back to the pool (stream ordered)
+    else cudaFree(pl->arena);
+  }
   if (pl->h_stage) cudaFreeHost(pl->h_stage);
   delete pl;
 }
@@ -267,7 +276,7 @@ static int upload(blance_ctx* ctx, int n, const blance_plan_in* ins, blance_plan
   }
   seg_off[n] = (int)pl->PT;
   pl->raw_rows_off[n] = pl->RRT; pl->raw_shape_off[n] = pl->RST;
-  if (pl->PT >= (1LL << 31)) { plan_release(pl); return fail(ctx, BLANCE_ERR_UNSUPPORTED, "2^31 or more partitions in one batch"); }
+  if (pl->PT >= (1LL << 31)) { plan_release(pl, ctx); return fail(ctx, BLANCE_ERR_UNSUPPORTED, "2^31 or more partitions in one batch"); }
 
   // ---- carve one device arena ------------------------------------------------------------
   struct Slice { void** ptr; size_t bytes; };
@@ -296,9 +305,10 @@ static int upload(blance_ctx* ctx, int n, const blance_plan_in* ins, blance_plan
 #undef SL_
   size_t total = 0;
   for (auto& s : slices) total += align_up(s.bytes, 256);
-  cudaError_t e = cudaMalloc(&pl->arena, total);
+  // stream-ordered allocation: the context's memory pool keeps the arena of the previous call around
+  cudaError_t e = cudaMallocAsync(&pl->arena, total, ctx->stream);
   if (e != cudaSuccess) {
-    plan_release(pl);
+    plan_release(pl, ctx);
     return fail(ctx, BLANCE_ERR_NOMEM, std::string("cudaMalloc of the plan arena failed: ") + cudaGetErrorString(e));
   }
   pl->arena_bytes = total;
@@ -336,7 +346,7 @@ static int upload(blance_ctx* ctx, int n, const blance_plan_in* ins, blance_plan
                              align_up(sizeof(int32_t) * NT, 256) * 3 + align_up(NT, 256) + align_up(sizeof(uint32_t) * MT, 256);
   e = cudaMallocHost(&pl->h_stage, stage_bytes);
   if (e != cudaSuccess) {
-    plan_release(pl);
+    plan_release(pl, ctx);
     return fail(ctx, BLANCE_ERR_NOMEM, std::string("cudaMallocHost of the staging buffer failed: ") + cudaGetErrorString(e));
   }
   pl->h_stage_bytes = stage_bytes;
@@ -388,7 +398,7 @@ static int upload(blance_ctx* ctx, int n, const blance_plan_in* ins, blance_plan
   cudaStream_t st = ctx->stream;
 #define H2D(dst, src, bytes) do { if ((bytes) > 0) { \
     e = (src) ? cudaMemcpyAsync((void*)(dst), (src), (bytes), cudaMemcpyHostToDevice, st) : cudaMemsetAsync((void*)(dst), 0, (bytes), st); \
-    if (e != cudaSuccess) { plan_release(pl); return fail(ctx, BLANCE_ERR_CUDA, std::string("H2D copy failed: ") + cudaGetErrorString(e)); } } } while (0)
+    if (e != cudaSuccess) { plan_release(pl, ctx); return fail(ctx, BLANCE_ERR_CUDA, std::string("H2D copy failed: ") + cudaGetErrorString(e)); } } } while (0)
   H2D(pl->raw_a, h_cur, sizeof(int32_t) * (size_t)pl->RRT); H2D(pl->raw_b, h_prev, sizeof(int32_t) * (size_t)pl->RRT);
   H2D(pl->rawsh_a, h_csh, (size_t)pl->RST); H2D(pl->rawsh_b, h_psh, (size_t)pl->RST);
   H2D(pl->pflags_init, h_flags, (size_t)pl->PT); H2D(c_pweight, h_pw, sizeof(int32_t) * (size_t)pl->PT);
@@ -408,12 +418,12 @@ static int upload(blance_ctx* ctx, int n, const blance_plan_in* ins, blance_plan
                                                         pl->d_raw_rows_off, pl->d_raw_shape_off, pl->PT);
     ctx->launches++;
     e = cudaGetLastError();
-    if (e != cudaSuccess) { plan_release(pl); return fail(ctx, BLANCE_ERR_CUDA, std::string("k_unpack launch failed: ") + cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { plan_release(pl, ctx); return fail(ctx, BLANCE_ERR_CUDA, std::string("k_unpack launch failed: ") + cudaGetErrorString(e)); }
     if (e == cudaSuccess) e = cudaMemcpyAsync(pl->rows_init, P.rows, sizeof(int32_t) * (size_t)pl->RT, cudaMemcpyDeviceToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(pl->prev_rows_init, P.prev_rows, sizeof(int32_t) * (size_t)pl->RT, cudaMemcpyDeviceToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(pl->pmeta_init, P.pmeta, sizeof(uint32_t) * (size_t)pl->PT, cudaMemcpyDeviceToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(pl->prev_meta_init, P.prev_meta, sizeof(uint32_t) * (size_t)pl->PT, cudaMemcpyDeviceToDevice, st);
-    if (e != cudaSuccess) { plan_release(pl); return fail(ctx, BLANCE_ERR_CUDA, std::string("upload failed: ") + cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { plan_release(pl, ctx); return fail(ctx, BLANCE_ERR_CUDA, std::string("upload failed: ") + cudaGetErrorString(e)); }
   }
   // sort scratch
   size_t need = 0, need2 = 0;
@@ -425,11 +435,11 @@ static int upload(blance_ctx* ctx, int n, const blance_plan_in* ins, blance_plan
     if (ctx->cub_tmp) cudaFree(ctx->cub_tmp);
     ctx->cub_tmp = nullptr; ctx->cub_tmp_bytes = 0;
     e = cudaMalloc(&ctx->cub_tmp, need);
-    if (e != cudaSuccess) { plan_release(pl); return fail(ctx, BLANCE_ERR_NOMEM, "cudaMalloc of the sort scratch failed"); }
+    if (e != cudaSuccess) { plan_release(pl, ctx); return fail(ctx, BLANCE_ERR_NOMEM, "cudaMalloc of the sort scratch failed"); }
     ctx->cub_tmp_bytes = need;
   }
   e = cudaStreamSynchronize(st);
-  if (e != cudaSuccess) { plan_release(pl); return fail(ctx, BLANCE_ERR_CUDA, std::string("upload sync failed: ") + cudaGetErrorString(e)); }
+  if (e != cudaSuccess) { plan_release(pl, ctx); return fail(ctx, BLANCE_ERR_CUDA, std::string("upload sync failed: ") + cudaGetErrorString(e)); }
   *out_plan = pl;
   return BLANCE_OK;
 }

@@ -14,7 +14,9 @@ fixtures - never at test time) and writes
                                      (plan_test.go:392-2863) and
                                      TestControlCase1-4 (control_test.go:18-416)
     tests/golden/moves_cases.json    TestFindStateChanges, TestCalcPartitionMoves
-                                     (moves_test.go:19-486)
+                                     (moves_test.go:19-486), and the per-partition move
+                                     sequences of TestOrchestrateMoves
+                                     (orchestrate_test.go:1049-1811)
     tests/golden/unit_cases.json     helper tables (plan_test.go:21-390,
                                      misc_test.go:18-89)
 
@@ -95,6 +97,8 @@ NAMED["PartitionModelState"] = ("struct", [("Priority", INT), ("Constraints", IN
 NAMED["PartitionModel"] = ("map", STRING, ("ptr", T_named("PartitionModelState")))
 NAMED["HierarchyRule"] = ("struct", [("IncludeLevel", INT), ("ExcludeLevel", INT)])
 NAMED["HierarchyRules"] = ("map", STRING, ("slice", ("ptr", T_named("HierarchyRule"))))
+NAMED["OrchestratorOptions"] = ("struct", [("MaxConcurrentPartitionMovesPerNode", INT), ("FavorMinNodes", BOOL)])
+NAMED["assignPartitionRec"] = ("struct", [("partition", STRING), ("node", STRING), ("state", STRING), ("op", STRING)])
 NAMED["VisTestCase"] = ("struct", [
     ("Ignore", BOOL), ("About", STRING), ("FromTo", ("slice", ("slice", STRING))),
     ("FromToPriority", BOOL), ("Nodes", ("slice", STRING)),
@@ -115,7 +119,7 @@ def zero(t):
         return None
     if t[0] == "struct":
         return {f: zero(ft) for f, ft in t[1]}
-    return {"string": "", "int": 0, "bool": False}[t[1]]
+    return {"string": "", "int": 0, "bool": False, "error": None}[t[1]]
 
 
 class Parser:
@@ -168,7 +172,7 @@ class Parser:
                     fields.append((n, ft))
                 self.accept(";")
             return ("struct", fields)
-        if val in ("string", "int", "bool"):
+        if val in ("string", "int", "bool", "error"):
             return ("basic", val)
         if kind == "id":
             return T_named(val)
@@ -194,6 +198,11 @@ class Parser:
             return self.parse_literal_body(t)
         if self.looks_like_type():
             t = self.parse_type()
+            if self.peek()[1] == "(":           # conversion such as []string(nil)
+                self.next()
+                v = self.parse_value(t)
+                self.expect(")")
+                return v
             return self.parse_literal_body(t)
         self.next()
         if kind == "str" or kind == "raw":
@@ -435,6 +444,42 @@ def moves_cases(env):
     return out
 
 
+def package_vars(toks, names):
+    """Top-level `var name = literal` declarations."""
+    env = {}
+    for i in range(len(toks) - 3):
+        if toks[i] == ("id", "var") and toks[i + 1][1] in names and toks[i + 2][1] == "=":
+            p = Parser(toks, env)
+            p.i = i + 3
+            env[toks[i + 1][1]] = p.parse_value()
+    return env
+
+
+def orchestrate_cases(toks):
+    """TestOrchestrateMoves (orchestrate_test.go:1049-1811): the fake callback records, per partition, the
+    (node, state) sequence the orchestrator applies, which is CalcPartitionMoves(states, beg[p], end[p],
+    options.FavorMinNodes) in order (orchestrate.go:263-287).  states = sortStateNames(model)."""
+    env = package_vars(toks, ("mrPartitionModel", "options1"))
+    body = func_body_tokens(toks, "TestOrchestrateMoves")
+    p = Parser(body, env)
+    assert p.peek()[1] == "tests"
+    p.next(); p.next()
+    tests = p.parse_value()
+    out = []
+    for idx, c in enumerate(tests):
+        if c["skip"] or not c["expectAssignPartitions"]:
+            continue
+        model = c["partitionModel"]
+        states = sorted(model, key=lambda k: (model[k]["Priority"], k))
+        for part, recs in sorted(c["expectAssignPartitions"].items()):
+            out.append({"index": idx, "label": c["label"], "partition": part, "states": states,
+                        "before": (c["begMap"].get(part) or {"NodesByState": {}})["NodesByState"],
+                        "after": (c["endMap"].get(part) or {"NodesByState": {}})["NodesByState"],
+                        "favorMinNodes": c["options"]["FavorMinNodes"],
+                        "exp": [{"node": r["node"], "state": r["state"]} for r in recs]})
+    return out
+
+
 def main():
     plan_toks = tokenize(open(os.path.join(REF, "plan_test.go")).read())
     cases = plan_table_cases(parse_test_func(plan_toks, "TestPlanNextMap")["tests"])
@@ -450,9 +495,11 @@ def main():
     mv_toks = tokenize(open(os.path.join(REF, "moves_test.go")).read())
     fsc = parse_test_func(mv_toks, "TestFindStateChanges")["tests"]
     mv = moves_cases(parse_test_func(mv_toks, "TestCalcPartitionMoves"))
+    orch = orchestrate_cases(tokenize(open(os.path.join(REF, "orchestrate_test.go")).read()))
     with open(os.path.join(OUT, "moves_cases.json"), "w") as f:
-        json.dump({"findStateChanges": fsc, "calcPartitionMoves": mv}, f, indent=1, sort_keys=True)
-    print("findStateChanges cases: %d, calcPartitionMoves cases: %d" % (len(fsc), len(mv)))
+        json.dump({"findStateChanges": fsc, "calcPartitionMoves": mv, "orchestrateDerived": orch}, f, indent=1, sort_keys=True)
+    print("findStateChanges cases: %d, calcPartitionMoves cases: %d, orchestrate-derived sequences: %d"
+          % (len(fsc), len(mv), len(orch)))
 
     units = {}
     for fn, key in (("TestFlattenNodesByState", "flattenNodesByState"),

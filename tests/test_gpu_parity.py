@@ -73,9 +73,17 @@ def test_calc_partition_moves_golden_gpu():
             assert op.Node == e["node"] and op.State == e["state"] and op.Op in e["op"], (c["index"], got, c["exp"])
 
 
+def test_orchestrate_derived_move_sequences_gpu():
+    for c in G.load("moves_cases.json")["orchestrateDerived"]:
+        got = blance_b200.CalcPartitionMoves(c["states"], c["before"], c["after"], c["favorMinNodes"])
+        assert len(got) >= len(c["exp"]), (c["label"], c["partition"])
+        for op, e in zip(got, c["exp"]):
+            assert op.Node == e["node"] and op.State == e["state"], (c["label"], c["partition"], got, c["exp"])
+
+
 # ---- randomised instances: same interned tables through CUDA and through the oracle ---------
 
-@pytest.mark.parametrize("chunk", range(8))
+@pytest.mark.parametrize("chunk", range(16))
 def test_random_instances_gpu_vs_oracle(chunk):
     L = literal()
     for seed in range(chunk * 60, (chunk + 1) * 60):
@@ -93,6 +101,72 @@ def test_random_instances_gpu_vs_oracle(chunk):
             lit = L.plan_next_map_ex(**copy.deepcopy(kw))
             r = _host.PlanNextMapEx(**copy.deepcopy(kw))
             assert r["next_map"] == lit["next_map"] and r["warnings"] == lit["warnings"], seed
+
+
+def random_tables(seed):
+    """Mid-size random flat instances (hundreds to thousands of partitions): large enough for the sequencer
+    kernel to be picked, with churn, weights, stickiness, partial assignment and nodes outside nodesAll."""
+    rng = np.random.default_rng(seed)
+    N = int(rng.integers(6, 160))
+    S = int(rng.integers(1, 4))
+    k = [int(rng.integers(1, 4)) if s < 2 else int(rng.integers(0, 2)) for s in range(S)]
+    while sum(k) > N - 2:
+        k = [max(1, x - 1) if s == 0 else max(0, x - 1) for s, x in enumerate(k)]
+    P = int(rng.integers(70, 2500))
+    NU = N + int(rng.integers(0, 3))
+    t = tables.PlanTables(N, S, P, list(range(S)), k, n_node_ids=NU)
+    SL = t.n_slots
+    rows = np.full((P, SL), -1, np.int32)
+    live = max(SL + 1, N - int(rng.integers(0, 4)))
+    for p in range(P):
+        perm = rng.permutation(live)[:SL]
+        for s in range(S):
+            lo, hi = int(t.state_slot_off[s]), int(t.state_slot_off[s + 1])
+            n = hi - lo if rng.random() < 0.9 else int(rng.integers(0, hi - lo + 1))
+            rows[p, lo:lo + n] = perm[lo:lo + n]
+    if NU > N and P > 3:
+        rows[1, SL - 1] = N            # a node name that is not in nodesAll
+    t.prev_rows[:] = rows
+    t.cur_rows[:] = rows
+    if rng.random() < 0.3:             # partitionsToAssign differs from prevMap for some rows
+        sel = rng.random(P) < 0.05
+        t.cur_rows[sel] = -1
+    sh = (np.ones((P, S)) * 2).astype(np.uint8)
+    t.prev_shape[:] = sh
+    t.cur_shape[:] = sh
+    t.part_in_prev[:] = 1
+    if rng.random() < 0.3:
+        t.part_in_assign[:] = (rng.random(P) < 0.8).astype(np.uint8)
+    n_rm = int(rng.integers(0, max(1, N // 8)))
+    t.node_removed[rng.permutation(N)[:n_rm]] = 1
+    t.node_added[rng.permutation(N)[:int(rng.integers(0, N // 4 + 1))]] = 1
+    t.add_is_nil = int(rng.random() < 0.1)
+    if rng.random() < 0.6:
+        t.has_node_weights = 1
+        t.node_has_weight[:] = (rng.random(N) < 0.8).astype(np.uint8)
+        t.node_weight[:] = rng.integers(-2, 7, N)
+        t.booster_kind = int(rng.random() < 0.5)
+    if rng.random() < 0.6:
+        t.has_part_weights = 1
+        t.part_has_weight[:] = (rng.random(P) < 0.4).astype(np.uint8)
+        t.part_weight[:] = rng.integers(1, 9, P)
+        t.state_has_stickiness[:] = (rng.random(S) < 0.7).astype(np.uint8)
+        t.state_stickiness[:] = rng.integers(0, 5, S)
+    t.max_iters = int(rng.integers(1, 6))
+    return t
+
+
+@pytest.mark.parametrize("chunk", range(6))
+def test_random_midsize_tables_gpu_vs_oracle(ctx, chunk):
+    for seed in range(chunk * 8, (chunk + 1) * 8):
+        t = random_tables(seed)
+        ref = oracle_tables(t)
+        for engine in (0, 1):
+            t.engine = engine
+            got = ctx.plan_next_map(t)
+            assert np.array_equal(got.next_rows, ref.next_rows), (seed, engine)
+            assert np.array_equal(got.next_shape, ref.next_shape) and np.array_equal(got.warn, ref.warn), (seed, engine)
+            assert (got.iters_run, got.converged, got.steps) == (ref.iters_run, ref.converged, ref.steps), (seed, engine)
 
 
 def test_all_nodes_removed_gives_nil_lists(ctx):

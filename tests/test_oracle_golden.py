@@ -42,6 +42,16 @@ def test_calc_partition_moves_golden():
             assert node == e["node"] and state == e["state"] and op in e["op"], (c["index"], got, c["exp"])
 
 
+def test_orchestrate_derived_move_sequences():
+    """orchestrate_test.go:1796-1808 compares the recorded (node, state) of each assignment with the
+    expected list, entry by entry (the recorded list may be longer)."""
+    for c in G.load("moves_cases.json")["orchestrateDerived"]:
+        got = L.calc_partition_moves(c["states"], c["before"], c["after"], c["favorMinNodes"])
+        assert len(got) >= len(c["exp"]), (c["label"], c["partition"])
+        for (node, state, _op), e in zip(got, c["exp"]):
+            assert node == e["node"] and state == e["state"], (c["label"], c["partition"], got, c["exp"])
+
+
 def test_unit_tables():
     u = G.load("unit_cases.json")
     for c in u["flattenNodesByState"]:
