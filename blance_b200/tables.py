@@ -98,6 +98,7 @@ class PlanResult:
     iters_run = property(lambda self: self.out.iters_run)
     converged = property(lambda self: self.out.converged)
     steps = property(lambda self: self.out.steps)
+    sticky_steps = property(lambda self: self.out.sticky_steps)
     device_ms = property(lambda self: self.out.device_ms)
     kernel_ms = property(lambda self: self.out.kernel_ms)
     pass_ms = property(lambda self: self.out.pass_ms)

@@ -148,6 +148,7 @@ typedef struct blance_plan_out {
   float device_ms;         /* GPU time of the whole call (events on the ctx stream), H2D/D2H included */
   float kernel_ms;         /* GPU time with tables resident (between the copies) */
   float pass_ms;           /* time inside the sequential assign passes only */
+  int64_t sticky_steps;    /* of `steps`: decided by the sequencer's sticky test without a full evaluation */
 } blance_plan_out;
 
 /* Host buffers in, host buffers out.  If prevMap and partitionsToAssign must be

@@ -301,6 +301,7 @@ FO_EXPORT int oracle_fast_plan_next_map_capped(const blance_plan_in* in, blance_
 
   out->iters_run = 0; out->converged = 0; out->steps = 0;
   out->device_ms = out->kernel_ms = out->pass_ms = 0.f;
+  out->sticky_steps = 0;
 
   for (int it = 0; it < in->max_iters; it++) {                      /* plan.go:32 */
     /* plan.go:83-88: working rows = partitionsToAssign rows minus removed nodes */

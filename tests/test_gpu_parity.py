@@ -211,7 +211,7 @@ def test_cfg2_4096x64_rack_rules(ctx):
 
 
 def test_cfg3_65536x256_three_states_zone_rack(ctx):
-    two_stage(ctx, 3, P=16384)
+    two_stage(ctx, 3)
 
 
 def test_cfg4_weights_stickiness_reduced(ctx):
