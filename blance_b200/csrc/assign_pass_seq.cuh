@@ -329,14 +329,17 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s) 
 
   // records stream into the ring with cp.async; `loaded` = first record not yet requested
   int loaded = 0;
+  // 16-byte chunks: a record is CH = REC/4 chunks, so one warp instruction moves 32/CH records
+  const int CH = REC >> 2, RPB = 32 / CH;       // chunks per record, records per warp pass
+  const int my_rec = lane / CH, my_chunk = lane - my_rec * CH;
   auto request_records = [&](int upto) {       // request records [loaded, min(upto, n_assign)) as one group
     const int hi = upto < n_assign ? upto : n_assign;
-    for (int step = loaded; step < hi; ++step) {            // one record per trip: lane = word (REC <= 40)
-      const uint32_t dst = ring_a + (uint32_t)(step % SEQ_RING) * (BL_REC_MAX * 4u);
-      const int32_t* src = stream + (size_t)step * REC;
-      if (lane < REC) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst + (uint32_t)lane * 4u), "l"(src + lane) : "memory");
-      if (lane + 32 < REC) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst + (uint32_t)(lane + 32) * 4u), "l"(src + lane + 32) : "memory");
-    }
+    if (my_rec < RPB)
+      for (int step = loaded + my_rec; step < hi; step += RPB) {
+        const uint32_t dst = ring_a + (uint32_t)(step % SEQ_RING) * (BL_REC_MAX * 4u) + (uint32_t)my_chunk * 16u;
+        const int32_t* src = stream + (size_t)step * REC + my_chunk * 4;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+      }
     asm volatile("cp.async.commit_group;" ::: "memory");
     if (hi > loaded) loaded = hi;
   };
@@ -355,13 +358,17 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s) 
   int need_calm = 0, served = 0;
   long long n_fast = 0;
 #ifdef BLANCE_PASS_TIMING
-  long long t_win = 0, n_win = 0, t_slow = 0, n_slow = 0, t_reb = 0, n_reb = 0;
+  long long t_win = 0, n_win = 0, t_slow = 0, n_slow = 0, t_reb = 0, n_reb = 0, wp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define WP(ix) do { const long long n_ = clock64(); wp[ix] += n_ - tl; tl = n_; } while (0)
+#else
+#define WP(ix) do { } while (0)
 #endif
 
   int i = 0;
   while (i < n_assign) {
 #ifdef BLANCE_PASS_TIMING
     long long t0 = clock64();
+    long long tl = t0;
 #endif
     // keep the ring >= 2*SEQ_AHEAD records ahead.  Invariant: loaded >= i + SEQ_AHEAD (a window is at most
     // SEQ_AHEAD = 32 steps), so the group requested here never holds a record of the current window and
@@ -386,6 +393,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s) 
     const bool row_clean = lds32(reca + (uint32_t)(SLP + 7) * 4u) != 0;
     const int32_t rowv[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 
+    WP(0);
     // step i itself decides whether the cache has to be rebuilt first
     const bool first_eligible = __shfl_sync(0xFFFFFFFFu, (int)(row_clean && n_cur == k), 0) != 0;
     if (first_eligible && g_len == 0 && calm >= need_calm) {
@@ -422,13 +430,16 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s) 
         for (int sl = 0; sl < 8; ++sl) blocked = blocked || (((slot_blocked >> sl) & 1u) && rowv[sl] == e.z);
         if (!blocked) { g_found = true; gk = ((unsigned long long)(uint32_t)e.x << 32) | (uint32_t)e.y; gp = (uint32_t)e.z; }
       }
+      WP(1);
       // + the increments of the earlier steps of this window that share my (top, node)
       const unsigned long long mk = eligible ? (((unsigned long long)(uint32_t)top << 32) | (uint32_t)c)
                                              : (0xFFFFFFFF00000000ull | (uint32_t)lane);
       const uint32_t same = __match_any_sync(0xFFFFFFFFu, mk);
       q += __popc(same & ((1u << lane) - 1u));
+      WP(2);
       unsigned long long mykey = ~0ull;
       if (eligible) mykey = key_from(m_cd, m_ff, m_wd, m_wy, (fl & NF_BOOST) != 0, has_nw, q, stick, qtab_a, Pd, Py);
+      WP(3);
       const bool ok_self = eligible && (fl & NF_VALID) != 0;
       bool okl = true;                          // every current node of my step is a live candidate
       // the k (key, node) pairs of my step: worst key of the step, my rank inside it
@@ -449,6 +460,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s) 
       bool accept = false;
       if (okl) accept = g_found ? (mxk < gk || (mxk == gk && (uint32_t)mxp < gp))
                                 : (g_complete != 0);   // every other live node is ineligible for this partition
+      WP(4);
       // commit the leading run of sticky steps
       const uint32_t rej = __ballot_sync(0xFFFFFFFFu, wlane && !accept);
       const int first_rej_lane = rej ? (__ffs(rej) - 1) : 32;
@@ -461,6 +473,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s) 
         if (wq == 0) orec[k] = k;
       }
       __syncwarp();                            // the REDs above are ordered before the next window's loads
+      WP(5);
       n_fast += n_acc;
       served += n_acc;
       calm = calm + n_acc < (1 << 30) ? calm + n_acc : (1 << 30);
@@ -491,6 +504,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s) 
 #endif
   }
 #ifdef BLANCE_PASS_TIMING
+  if (lane == 0 && blockIdx.x == 0)
+    printf("   window phases (cycles per window): ring+record loads %.0f | mirror+n2n issue+cache scan %.0f | match %.0f | key %.0f | exchange+accept %.0f | ballot+commit %.0f\n",
+           (double)wp[0] / (n_win ? n_win : 1), (double)wp[1] / (n_win ? n_win : 1), (double)wp[2] / (n_win ? n_win : 1), (double)wp[3] / (n_win ? n_win : 1),
+           (double)wp[4] / (n_win ? n_win : 1), (double)wp[5] / (n_win ? n_win : 1));
   if (lane == 0 && blockIdx.x == 0)
     printf("seq pass s=%d steps %d: sticky %lld in %lld windows (%.0f cyc/window, %.1f steps/window); full %lld (%.0f cyc each); rebuilds %lld (%.0f cyc each)\n",
            s, n_assign, n_fast, n_win, n_win ? (double)t_win / n_win : 0.0, n_win ? (double)n_fast / n_win : 0.0, n_slow,
