@@ -120,11 +120,11 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s) 
   int32_t* n2n = pool.n2n + D.n2n_off;
   const int32_t* extra = (D.use_rest ? pool.extra_rest : pool.extra_first) + D.node_off;
 
-  double* nd_cd = reinterpret_cast<double*>(dyn_smem);
-  double* nd_ff = nd_cd + N;
-  double* nd_wd = nd_ff + N;
-  double* nd_wy = nd_wd + N;
-  uint8_t* nd_flag = reinterpret_cast<uint8_t*>(nd_wy + N);
+  // mirror of the per-node score inputs: 32 bytes per node {cd, ff, wd, wy}, then one flag byte per node
+  double* nd = reinterpret_cast<double*>(dyn_smem);
+  uint8_t* nd_flag = reinterpret_cast<uint8_t*>(nd + 4 * (size_t)N);
+  const uint32_t nd_a = (uint32_t)__cvta_generic_to_shared(dyn_smem);
+  const uint32_t ndf_a = nd_a + 32u * (uint32_t)N;
 
   const uint32_t sm_a = (uint32_t)__cvta_generic_to_shared(&sm);
   const uint32_t ring_a = sm_a + (uint32_t)offsetof(SeqSmem, ring);
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s) 
         else if (w < 0 && D.booster == BLANCE_BOOSTER_CBGT_MAX) { boost_bits |= 1u << j; wd[j] = (double)w; }
       }                                                                            // w == 0 / no booster: untouched
       if (Pn > 0) ff[j] = div_exact(__dmul_rn(0.001, (double)t), Pd, Py);          // plan.go:650
-      nd_cd[n] = cd[j]; nd_ff[n] = ff[j]; nd_wd[n] = wd[j]; nd_wy[n] = wy[j];
+      nd[4 * n] = cd[j]; nd[4 * n + 1] = ff[j]; nd[4 * n + 2] = wd[j]; nd[4 * n + 3] = wy[j];
       nd_flag[n] = (uint8_t)((((valid_bits >> j) & 1u) ? NF_VALID : 0u) | (((boost_bits >> j) & 1u) ? NF_BOOST : 0u));
     }
   }
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s) 
             tot[j] = t;
             if (Pn > 0) ff[j] = div_exact(__dmul_rn(0.001, (double)t), Pd, Py);
           }
-          nd_cd[n] = cd[j]; nd_ff[n] = ff[j];
+          nd[4 * n] = cd[j]; nd[4 * n + 1] = ff[j];
           Lk[j] = key_from(cd[j], ff[j], wd[j], wy[j], (boost_bits >> j) & 1u, has_nw, 0, 0.0, qtab_a, Pd, Py);
         }
       }
@@ -416,9 +416,13 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s) 
       for (int sl = 0; sl < 8; ++sl) c = (sl == lo_s + wq) ? rowv[sl] : c;
       if (!eligible) c = -1;
       const int cc = c < 0 ? 0 : c;            // row_clean: 0 <= c < N
-      const double m_cd = nd_cd[cc], m_ff = nd_ff[cc], m_wd = nd_wd[cc], m_wy = nd_wy[cc];
-      const uint32_t fl = nd_flag[cc];
-      int32_t q = (eligible && Pn > 0) ? __ldcg(n2n + (size_t)top * N + cc) : 0;    // L2 latency, overlapped below
+      // n2n first (L2 latency, overlapped with everything up to the key), then the mirror
+      int32_t q = (eligible && Pn > 0) ? __ldcg(n2n + (size_t)top * N + cc) : 0;
+      const int4 ma = lds128(nd_a + (uint32_t)cc * 32u), mb = lds128(nd_a + (uint32_t)cc * 32u + 16u);
+      const double m_cd = __hiloint2double(ma.y, ma.x), m_ff = __hiloint2double(ma.w, ma.z);
+      const double m_wd = __hiloint2double(mb.y, mb.x), m_wy = __hiloint2double(mb.w, mb.z);
+      uint32_t fl;
+      asm volatile("ld.shared.u8 %0, [%1];" : "=r"(fl) : "r"(ndf_a + (uint32_t)cc));
       // smallest cached base key among the nodes this row does not block (independent of q)
       bool g_found = false;
       unsigned long long gk = 0;
@@ -446,6 +450,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s) 
       unsigned long long mxk = mykey;
       int32_t mxp = c;
       int rank = 0;
+      if (K == 1) okl = ok_self;
+      if (K > 1)
 #pragma unroll
       for (int t = 0; t < K; ++t) {
         const unsigned long long ok_ = __shfl_sync(0xFFFFFFFFu, mykey, gb + t);
