@@ -35,6 +35,7 @@ namespace blance_dev {
 #define BL_CALM_MIN 3      // rebuild the cache only after this many steps without a count change
 #define SEQ_RING 128       // step-record ring of the sequencer kernel (records)
 #define SEQ_AHEAD 32       // records are requested (cp.async) at least this many steps ahead
+#define SEQ_DUP_LOG 13     // (top, node) duplicate filter of a window: 2^13 one-byte buckets
 
 enum : int32_t { SEQ_CMD_EXIT = -1, SEQ_CMD_REBUILD = -2 };
 enum : int { BAR_GO = 1, BAR_DONE = 2, BAR_ROUND = 3 };
@@ -50,6 +51,7 @@ struct SeqSmem {
   int32_t res_n, res_same;
   int32_t res_chosen[BL_K_MAX];
   int32_t g_len, g_complete;
+  alignas(16) uint8_t dup[1 << SEQ_DUP_LOG];
 };
 
 // per-node mirror in dynamic shared memory: cd, ff, wd, wy (doubles) and a flag byte
@@ -132,6 +134,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s) 
   const uint32_t qtab_a = sm_a + (uint32_t)offsetof(SeqSmem, qtab);
   const uint32_t sbit_a = sm_a + (uint32_t)offsetof(SeqSmem, slot_bit);
   const uint32_t glist_a = sm_a + (uint32_t)offsetof(SeqSmem, glist);
+  const uint32_t dup_a = sm_a + (uint32_t)offsetof(SeqSmem, dup);
 
   // ---- pass constants ---------------------------------------------------------------------
   for (int i = tid; i < SLP; i += NT) {
@@ -323,7 +326,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s) 
   // is not sticky, which goes to the compute warps, and the next window starts right after it.
   // SIMD across STEPS instead of across nodes: one warp pass (one FP64 latency chain) decides up to 32
   // steps.  (Rows have SLP <= 8 here: k_pick_mode.)
-  constexpr int WS = 32 / K;                    // steps per window
+  constexpr int WS = 32 / K;                    // steps per sub-window (one (step, node) item per lane)
+  constexpr int U = K >= 2 ? 2 : 1;             // sub-windows per window: every lane carries U items (ILP)
+  constexpr int WT = WS * U;                    // steps per window (<= SEQ_AHEAD)
   const int wstep = lane / k, wq = lane - wstep * k, gb = wstep * k;
   const bool wlane = wstep < WS;
 
@@ -353,22 +358,22 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s) 
     if ((uint32_t)lds32(sbit_a + (uint32_t)sl * 4u) & blk_mask) slot_blocked |= 1u << sl;
 
   int g_len = 0, g_complete = 0, calm = BL_CALM_MIN;
+  // the cached list is the same for every lane and changes only at a rebuild: its nodes stay in registers
+  uint32_t gpos[BL_GLIST];
+#pragma unroll
+  for (int g = 0; g < BL_GLIST; ++g) gpos[g] = 0xFFFFFFFFu;
   // How many quiet steps to wait before rebuilding the cache: none while rebuilds pay off (the
   // cache served at least 8 sticky steps before it was dropped), up to BL_CALM_MIN otherwise.
   int need_calm = 0, served = 0;
   long long n_fast = 0;
 #ifdef BLANCE_PASS_TIMING
-  long long t_win = 0, n_win = 0, t_slow = 0, n_slow = 0, t_reb = 0, n_reb = 0, wp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#define WP(ix) do { const long long n_ = clock64(); wp[ix] += n_ - tl; tl = n_; } while (0)
-#else
-#define WP(ix) do { } while (0)
+  long long t_win = 0, n_win = 0, t_slow = 0, n_slow = 0, n_slow_same = 0, t_reb = 0, n_reb = 0, n_cut = 0;
 #endif
 
   int i = 0;
   while (i < n_assign) {
 #ifdef BLANCE_PASS_TIMING
     long long t0 = clock64();
-    long long tl = t0;
 #endif
     // keep the ring >= 2*SEQ_AHEAD records ahead.  Invariant: loaded >= i + SEQ_AHEAD (a window is at most
     // SEQ_AHEAD = 32 steps), so the group requested here never holds a record of the current window and
@@ -381,21 +386,30 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s) 
     }
     __syncwarp();
 
-    // ---- my step of the window, my current node ---------------------------------------------------------
-    const int j = i + wstep;
-    const bool live = wlane && j < n_assign;
-    const uint32_t reca = ring_a + (uint32_t)((live ? j : i) % SEQ_RING) * (BL_REC_MAX * 4u);
-    const int4 r0 = lds128(reca);                                            // slots 0..3
-    const int4 r1 = SLP > 4 ? lds128(reca + 16u) : make_int4(-1, -1, -1, -1);   // slots 4..7
-    const int32_t top = lds32(reca + (uint32_t)(SLP + 2) * 4u);
-    const double stick = lds64f(reca + (uint32_t)SLP * 4u + 16u);
-    const int n_cur = lds32(reca + (uint32_t)(SLP + 6) * 4u);
-    const bool row_clean = lds32(reca + (uint32_t)(SLP + 7) * 4u) != 0;
-    const int32_t rowv[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+    // ---- my U steps of the window (sub-window u holds steps i + u*WS ...), my current node --------------------
+    int jst[U];
+    bool eligible[U];
+    int32_t top[U], rowv[U][8], c[U];
+    double stick[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      jst[u] = i + u * WS + wstep;
+      const bool live = wlane && jst[u] < n_assign;
+      const uint32_t reca = ring_a + (uint32_t)((live ? jst[u] : i) % SEQ_RING) * (BL_REC_MAX * 4u);
+      const int4 r0 = lds128(reca);                                            // slots 0..3
+      const int4 r1 = SLP > 4 ? lds128(reca + 16u) : make_int4(-1, -1, -1, -1);   // slots 4..7
+      top[u] = lds32(reca + (uint32_t)(SLP + 2) * 4u);
+      stick[u] = lds64f(reca + (uint32_t)SLP * 4u + 16u);
+      const int n_cur = lds32(reca + (uint32_t)(SLP + 6) * 4u);
+      const bool row_clean = lds32(reca + (uint32_t)(SLP + 7) * 4u) != 0;
+      rowv[u][0] = r0.x; rowv[u][1] = r0.y; rowv[u][2] = r0.z; rowv[u][3] = r0.w;
+      rowv[u][4] = r1.x; rowv[u][5] = r1.y; rowv[u][6] = r1.z; rowv[u][7] = r1.w;
+      eligible[u] = live && row_clean && n_cur == k;
+      c[u] = lds32(reca + (uint32_t)(lo_s + wq) * 4u);                         // my current node
+    }
 
-    WP(0);
     // step i itself decides whether the cache has to be rebuilt first
-    const bool first_eligible = __shfl_sync(0xFFFFFFFFu, (int)(row_clean && n_cur == k), 0) != 0;
+    const bool first_eligible = __shfl_sync(0xFFFFFFFFu, (int)eligible[0], 0) != 0;
     if (first_eligible && g_len == 0 && calm >= need_calm) {
       served = 0;
       if (lane == 0) *(volatile int32_t*)&sm.cmd = SEQ_CMD_REBUILD;
@@ -403,6 +417,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s) 
       bar_sync(BAR_DONE, NT);
       g_len = *(volatile int32_t*)&sm.g_len;
       g_complete = *(volatile int32_t*)&sm.g_complete;
+#pragma unroll
+      for (int g = 0; g < BL_GLIST; ++g) gpos[g] = (uint32_t)lds32(glist_a + (uint32_t)g * 16u + 8u);
 #ifdef BLANCE_PASS_TIMING
       { long long t1 = clock64(); t_reb += t1 - t0; t0 = t1; ++n_reb; }
 #endif
@@ -410,84 +426,133 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s) 
 
     int n_acc = 0;                              // leading sticky steps of this window
     if (first_eligible && g_len > 0) {
-      const bool eligible = live && row_clean && n_cur == k;
-      int32_t c = -1;
-#pragma unroll
-      for (int sl = 0; sl < 8; ++sl) c = (sl == lo_s + wq) ? rowv[sl] : c;
-      if (!eligible) c = -1;
-      const int cc = c < 0 ? 0 : c;            // row_clean: 0 <= c < N
+      int32_t q[U];
+      int4 ma[U], mb[U];
+      uint32_t fl[U], hb[U];
       // n2n first (L2 latency, overlapped with everything up to the key), then the mirror
-      int32_t q = (eligible && Pn > 0) ? __ldcg(n2n + (size_t)top * N + cc) : 0;
-      const int4 ma = lds128(nd_a + (uint32_t)cc * 32u), mb = lds128(nd_a + (uint32_t)cc * 32u + 16u);
-      const double m_cd = __hiloint2double(ma.y, ma.x), m_ff = __hiloint2double(ma.w, ma.z);
-      const double m_wd = __hiloint2double(mb.y, mb.x), m_wy = __hiloint2double(mb.w, mb.z);
-      uint32_t fl;
-      asm volatile("ld.shared.u8 %0, [%1];" : "=r"(fl) : "r"(ndf_a + (uint32_t)cc));
-      // smallest cached base key among the nodes this row does not block (independent of q)
-      bool g_found = false;
-      unsigned long long gk = 0;
-      uint32_t gp = 0;
-      for (int g = 0; g < g_len && !g_found; ++g) {
-        const int4 e = lds128(glist_a + (uint32_t)g * 16u);
-        bool blocked = false;
 #pragma unroll
-        for (int sl = 0; sl < 8; ++sl) blocked = blocked || (((slot_blocked >> sl) & 1u) && rowv[sl] == e.z);
-        if (!blocked) { g_found = true; gk = ((unsigned long long)(uint32_t)e.x << 32) | (uint32_t)e.y; gp = (uint32_t)e.z; }
+      for (int u = 0; u < U; ++u) {
+        if (!eligible[u]) c[u] = -1;
+        const int cc = c[u] < 0 ? 0 : c[u];     // row_clean: 0 <= c < N
+        q[u] = (eligible[u] && Pn > 0) ? __ldcg(n2n + (size_t)top[u] * N + cc) : 0;
+        ma[u] = lds128(nd_a + (uint32_t)cc * 32u);
+        mb[u] = lds128(nd_a + (uint32_t)cc * 32u + 16u);
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(fl[u]) : "r"(ndf_a + (uint32_t)cc));
+        // (top, node) pairs repeated inside a window are rare: a one-byte-per-bucket filter in shared memory
+        // (last writer wins, stale bytes are overwritten by my own store) proves their absence
+        hb[u] = dup_a + ((((uint32_t)top[u] * 0x9E3779B1u) ^ ((uint32_t)c[u] * 0x85EBCA77u)) >> (32 - SEQ_DUP_LOG));
+        if (eligible[u]) asm volatile("st.shared.u8 [%0], %1;" :: "r"(hb[u]), "r"(u * 32 + lane) : "memory");
       }
-      WP(1);
-      // + the increments of the earlier steps of this window that share my (top, node)
-      const unsigned long long mk = eligible ? (((unsigned long long)(uint32_t)top << 32) | (uint32_t)c)
-                                             : (0xFFFFFFFF00000000ull | (uint32_t)lane);
-      const uint32_t same = __match_any_sync(0xFFFFFFFFu, mk);
-      q += __popc(same & ((1u << lane) - 1u));
-      WP(2);
-      unsigned long long mykey = ~0ull;
-      if (eligible) mykey = key_from(m_cd, m_ff, m_wd, m_wy, (fl & NF_BOOST) != 0, has_nw, q, stick, qtab_a, Pd, Py);
-      WP(3);
-      const bool ok_self = eligible && (fl & NF_VALID) != 0;
-      bool okl = true;                          // every current node of my step is a live candidate
-      // the k (key, node) pairs of my step: worst key of the step, my rank inside it
-      unsigned long long mxk = mykey;
-      int32_t mxp = c;
-      int rank = 0;
-      if (K == 1) okl = ok_self;
-      if (K > 1)
+      // smallest cached base key among the nodes my row does not block (independent of q)
+      bool g_found[U];
+      unsigned long long gk[U];
+      uint32_t gp[U];
 #pragma unroll
-      for (int t = 0; t < K; ++t) {
-        const unsigned long long ok_ = __shfl_sync(0xFFFFFFFFu, mykey, gb + t);
-        const int32_t oc = __shfl_sync(0xFFFFFFFFu, c, gb + t);
-        const bool okt = __shfl_sync(0xFFFFFFFFu, (int)ok_self, gb + t) != 0;
-        okl = okl && okt;
-        if (t != wq) {
-          if (ok_ < mykey || (ok_ == mykey && oc < c)) ++rank;
-          if (ok_ > mxk || (ok_ == mxk && oc > mxp)) { mxk = ok_; mxp = oc; }
+      for (int u = 0; u < U; ++u) {
+        g_found[u] = false; gk[u] = 0; gp[u] = 0;
+        int gi = -1;
+        int32_t bn[8];                          // the nodes this row blocks
+#pragma unroll
+        for (int sl = 0; sl < 8; ++sl) bn[sl] = ((slot_blocked >> sl) & 1u) ? rowv[u][sl] : -2;
+#pragma unroll
+        for (int g = BL_GLIST - 1; g >= 0; --g)
+          if (g < g_len) {
+            bool blocked = false;
+#pragma unroll
+            for (int sl = 0; sl < 8; ++sl) blocked = blocked || (bn[sl] == (int32_t)gpos[g]);
+            if (!blocked) gi = g;
+          }
+        if (gi >= 0) {
+          const int4 e = lds128(glist_a + (uint32_t)gi * 16u);
+          g_found[u] = true;
+          gk[u] = ((unsigned long long)(uint32_t)e.x << 32) | (uint32_t)e.y;
+          gp[u] = (uint32_t)e.z;
         }
       }
-      bool accept = false;
-      if (okl) accept = g_found ? (mxk < gk || (mxk == gk && (uint32_t)mxp < gp))
-                                : (g_complete != 0);   // every other live node is ineligible for this partition
-      WP(4);
-      // commit the leading run of sticky steps
-      const uint32_t rej = __ballot_sync(0xFFFFFFFFu, wlane && !accept);
-      const int first_rej_lane = rej ? (__ffs(rej) - 1) : 32;
-      n_acc = first_rej_lane / k;
-      if (n_acc > WS) n_acc = WS;
-      if (wlane && wstep < n_acc) {
-        atomicAdd(&n2n[(size_t)top * N + c], 1);                   // plan.go:238-245
-        int32_t* orec = ostream + (size_t)j * REC;
-        orec[rank] = c;                                            // ordered by (score, position)
-        if (wq == 0) orec[k] = k;
+      // + the increments of the earlier steps of this window that share my (top, node): none unless two items
+      // met in a filter bucket; then only sub-window 0 is decided, with match.any counting the repeats
+      __syncwarp();
+      bool coll = false;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        uint32_t seen = (uint32_t)(u * 32 + lane);
+        if (eligible[u]) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(seen) : "r"(hb[u]) : "memory");
+        coll = coll || seen != (uint32_t)(u * 32 + lane);
       }
+      const bool cut = __any_sync(0xFFFFFFFFu, coll);
+      if (cut) {
+        const unsigned long long mk = eligible[0] ? (((unsigned long long)(uint32_t)top[0] << 32) | (uint32_t)c[0])
+                                                  : (0xFFFFFFFF00000000ull | (uint32_t)lane);
+        const uint32_t same = __match_any_sync(0xFFFFFFFFu, mk);
+        q[0] += __popc(same & ((1u << lane) - 1u));
+      }
+      bool accept[U];
+      int rank[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        unsigned long long mykey = ~0ull;
+        if (eligible[u])
+          mykey = key_from(__hiloint2double(ma[u].y, ma[u].x), __hiloint2double(ma[u].w, ma[u].z), __hiloint2double(mb[u].y, mb[u].x),
+                           __hiloint2double(mb[u].w, mb[u].z), (fl[u] & NF_BOOST) != 0, has_nw, q[u], stick[u], qtab_a, Pd, Py);
+        const bool ok_self = eligible[u] && (fl[u] & NF_VALID) != 0;
+        bool okl = true;                        // every current node of my step is a live candidate
+        // the k (key, node) pairs of my step: worst key of the step, my rank inside it
+        unsigned long long mxk = mykey;
+        int32_t mxp = c[u];
+        rank[u] = 0;
+        if (K == 1) okl = ok_self;
+        if (K == 2) {                           // the other lane of my pair
+          const unsigned long long ok_ = __shfl_xor_sync(0xFFFFFFFFu, mykey, 1);
+          const int32_t oc = __shfl_xor_sync(0xFFFFFFFFu, ok_self ? c[u] : -1, 1);
+          okl = ok_self && oc >= 0;
+          if (ok_ < mykey || (ok_ == mykey && oc < c[u])) rank[u] = 1;
+          if (ok_ > mxk || (ok_ == mxk && oc > mxp)) { mxk = ok_; mxp = oc; }
+        }
+        if (K > 2)
+#pragma unroll
+        for (int t = 0; t < K; ++t) {
+          const unsigned long long ok_ = __shfl_sync(0xFFFFFFFFu, mykey, gb + t);
+          const int32_t oc = __shfl_sync(0xFFFFFFFFu, c[u], gb + t);
+          const bool okt = __shfl_sync(0xFFFFFFFFu, (int)ok_self, gb + t) != 0;
+          okl = okl && okt;
+          if (t != wq) {
+            if (ok_ < mykey || (ok_ == mykey && oc < c[u])) ++rank[u];
+            if (ok_ > mxk || (ok_ == mxk && oc > mxp)) { mxk = ok_; mxp = oc; }
+          }
+        }
+        accept[u] = false;
+        if (okl) accept[u] = g_found[u] ? (mxk < gk[u] || (mxk == gk[u] && (uint32_t)mxp < gp[u]))
+                                        : (g_complete != 0);   // every other live node is ineligible for this partition
+      }
+      // commit the leading run of sticky steps
+      n_acc = 0;
+      bool open = true;                         // no rejected step so far
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t rej = (u > 0 && cut) ? 0xFFFFFFFFu : __ballot_sync(0xFFFFFFFFu, wlane && !accept[u]);
+        int a = (rej ? (__ffs(rej) - 1) : 32) / k;
+        if (a > WS) a = WS;
+        if (open) n_acc += a;
+        open = open && a == WS;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (wlane && u * WS + wstep < n_acc) {
+          atomicAdd(&n2n[(size_t)top[u] * N + c[u]], 1);               // plan.go:238-245
+          int32_t* orec = ostream + (size_t)jst[u] * REC;
+          orec[rank[u]] = c[u];                                      // ordered by (score, position)
+          if (wq == 0) orec[k] = k;
+        }
       __syncwarp();                            // the REDs above are ordered before the next window's loads
-      WP(5);
       n_fast += n_acc;
       served += n_acc;
       calm = calm + n_acc < (1 << 30) ? calm + n_acc : (1 << 30);
       i += n_acc;
 #ifdef BLANCE_PASS_TIMING
-      { long long t1 = clock64(); t_win += t1 - t0; t0 = t1; ++n_win; }
+      { long long t1 = clock64(); t_win += t1 - t0; t0 = t1; ++n_win; n_cut += cut ? 1 : 0; }
 #endif
-      if (n_acc == WS || i >= n_assign) continue;                  // whole window sticky
+      // whole window sticky, or cut short by the filter (the next step is not known to be a reject)
+      if (n_acc == WT || i >= n_assign || (U > 1 && cut && n_acc == WS)) continue;
     }
     // ---- step i is not sticky (or there is no cache): full evaluation by the compute warps ---------------
     if (lane == 0) *(volatile int32_t*)&sm.cmd = i;
@@ -506,18 +571,14 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s) 
     }
     ++i;
 #ifdef BLANCE_PASS_TIMING
-    { long long t1 = clock64(); t_slow += t1 - t0; ++n_slow; }
+    { long long t1 = clock64(); t_slow += t1 - t0; ++n_slow; n_slow_same += *(volatile int32_t*)&sm.res_same ? 1 : 0; }
 #endif
   }
 #ifdef BLANCE_PASS_TIMING
   if (lane == 0 && blockIdx.x == 0)
-    printf("   window phases (cycles per window): ring+record loads %.0f | mirror+n2n issue+cache scan %.0f | match %.0f | key %.0f | exchange+accept %.0f | ballot+commit %.0f\n",
-           (double)wp[0] / (n_win ? n_win : 1), (double)wp[1] / (n_win ? n_win : 1), (double)wp[2] / (n_win ? n_win : 1), (double)wp[3] / (n_win ? n_win : 1),
-           (double)wp[4] / (n_win ? n_win : 1), (double)wp[5] / (n_win ? n_win : 1));
-  if (lane == 0 && blockIdx.x == 0)
-    printf("seq pass s=%d steps %d: sticky %lld in %lld windows (%.0f cyc/window, %.1f steps/window); full %lld (%.0f cyc each); rebuilds %lld (%.0f cyc each)\n",
+    printf("seq pass s=%d steps %d: sticky %lld in %lld windows (%.0f cyc/window, %.1f steps/window); full %lld (%.0f cyc each, %lld kept the row); rebuilds %lld (%.0f cyc each); %lld windows cut by the filter\n",
            s, n_assign, n_fast, n_win, n_win ? (double)t_win / n_win : 0.0, n_win ? (double)n_fast / n_win : 0.0, n_slow,
-           n_slow ? (double)t_slow / n_slow : 0.0, n_reb, n_reb ? (double)t_reb / n_reb : 0.0);
+           n_slow ? (double)t_slow / n_slow : 0.0, n_slow_same, n_reb, n_reb ? (double)t_reb / n_reb : 0.0, n_cut);
 #endif
   if (lane == 0) *(volatile int32_t*)&sm.cmd = SEQ_CMD_EXIT;
   bar_sync(BAR_GO, NT);
