@@ -462,7 +462,7 @@ static void launch_pass(const DPool& P, int n_inst, int T, int s, bool hier, cud
 // the sequencer variant, one instantiation per constraint count K; CTAs whose instance picked the other
 // kernel (or has a different K for this state) exit at once
 template <int NPT, int K, int MAXT>
-static cudaError_t launch_pass_seq_k(size_t* configured, const DPool& P, int n_inst, int T, int s, size_t dyn, cudaStream_t st) {
+static cudaError_t launch_pass_seq_k(size_t* configured, const DPool& P, int n_inst, int TC, int W, int s, size_t dyn, cudaStream_t st) {
   {
     std::lock_guard<std::mutex> g(g_seq_dyn_mu);
     if (dyn > *configured) {
@@ -471,19 +471,19 @@ static cudaError_t launch_pass_seq_k(size_t* configured, const DPool& P, int n_i
       *configured = dyn;
     }
   }
-  k_assign_pass_seq<NPT, K, MAXT><<<n_inst, T, dyn, st>>>(P, s);
+  k_assign_pass_seq<NPT, K, MAXT><<<n_inst, TC + 32 * W, dyn, st>>>(P, s, TC);
   return cudaSuccess;
 }
 
 // kmask: bit K set when some instance of the batch has constraints == K for state s
 template <int NPT, int MAXT>
-static cudaError_t launch_pass_seq(size_t* configured, const DPool& P, int n_inst, int T, int s, int max_n, unsigned kmask, cudaStream_t st) {
-  const size_t dyn = (size_t)max_n * 33 + 16;
+static cudaError_t launch_pass_seq(size_t* configured, const DPool& P, int n_inst, int TC, int W, int s, int max_n, unsigned kmask, cudaStream_t st) {
+  const size_t dyn = seq_dyn_smem_bytes(max_n, W);
   cudaError_t e = cudaSuccess;
-  if (e == cudaSuccess && (kmask & 2u)) e = launch_pass_seq_k<NPT, 1, MAXT>(configured + 0, P, n_inst, T, s, dyn, st);
-  if (e == cudaSuccess && (kmask & 4u)) e = launch_pass_seq_k<NPT, 2, MAXT>(configured + 1, P, n_inst, T, s, dyn, st);
-  if (e == cudaSuccess && (kmask & 8u)) e = launch_pass_seq_k<NPT, 3, MAXT>(configured + 2, P, n_inst, T, s, dyn, st);
-  if (e == cudaSuccess && (kmask & 16u)) e = launch_pass_seq_k<NPT, 4, MAXT>(configured + 3, P, n_inst, T, s, dyn, st);
+  if (e == cudaSuccess && (kmask & 2u)) e = launch_pass_seq_k<NPT, 1, MAXT>(configured + 0, P, n_inst, TC, W, s, dyn, st);
+  if (e == cudaSuccess && (kmask & 4u)) e = launch_pass_seq_k<NPT, 2, MAXT>(configured + 1, P, n_inst, TC, W, s, dyn, st);
+  if (e == cudaSuccess && (kmask & 8u)) e = launch_pass_seq_k<NPT, 3, MAXT>(configured + 2, P, n_inst, TC, W, s, dyn, st);
+  if (e == cudaSuccess && (kmask & 16u)) e = launch_pass_seq_k<NPT, 4, MAXT>(configured + 3, P, n_inst, TC, W, s, dyn, st);
   return e;
 }
 
@@ -569,10 +569,13 @@ static int run(blance_ctx* ctx, blance_plan* pl) {
       cudaError_t se = cudaSuccess;
       unsigned kmask = 0;
       for (int i = 0; i < n; ++i) { const int kk = pl->h_insts[i].S > s ? pl->h_insts[i].state_constraints[s] : 0; if (kk >= 1 && kk <= 4) kmask |= 1u << kk; }
-      if (npt == 1) se = (launch_pass_seq<1, 544>)(g_seq_dyn[ctx->device & 63][0], P, n, T + 32, s, pl->max_N, kmask, st);
-      else if (npt == 2) se = (launch_pass_seq<2, 544>)(g_seq_dyn[ctx->device & 63][1], P, n, T + 32, s, pl->max_N, kmask, st);
-      else if (npt == 4) se = (launch_pass_seq<4, 544>)(g_seq_dyn[ctx->device & 63][2], P, n, T + 32, s, pl->max_N, kmask, st);
-      else if (npt == 8) se = (launch_pass_seq<8, 544>)(g_seq_dyn[ctx->device & 63][3], P, n, T + 32, s, pl->max_N, kmask, st);
+      // sequencer warps per CTA: wide windows when the GPU has SMs to spare, one warp for wide batches
+      int seq_w = (2 * n <= ctx->sm_count) ? SEQ_W_MAX : 1;
+      if (const char* ev = getenv("BLANCE_SEQ_W")) { const int v = atoi(ev); if (v >= 1 && v <= SEQ_W_MAX) seq_w = v; }   // experiments
+      if (npt == 1) se = (launch_pass_seq<1, 640>)(g_seq_dyn[ctx->device & 63][0], P, n, T, seq_w, s, pl->max_N, kmask, st);
+      else if (npt == 2) se = (launch_pass_seq<2, 640>)(g_seq_dyn[ctx->device & 63][1], P, n, T, seq_w, s, pl->max_N, kmask, st);
+      else if (npt == 4) se = (launch_pass_seq<4, 640>)(g_seq_dyn[ctx->device & 63][2], P, n, T, seq_w, s, pl->max_N, kmask, st);
+      else if (npt == 8) se = (launch_pass_seq<8, 640>)(g_seq_dyn[ctx->device & 63][3], P, n, T, seq_w, s, pl->max_N, kmask, st);
       CK(se);
       CK(cudaGetLastError());
       ctx->launches += 1 + (npt <= 8 ? __builtin_popcount(kmask) : 0);   // k_pick_mode + the sequencer kernel(s)
