@@ -629,10 +629,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s, 
       }
       if (winner[u]) { sm.dtab[slot[u]] = ~0ull; sm.dmin[slot[u]] = 0xFFFFFFFFu; }
     }
-    // a hand-off to the compute warps follows unless the whole window was sticky: their n2n loads must see
-    // the increments of every sequencer warp (window -> window is ordered by BAR_W0)
+    // a hand-off to the compute warps may follow (even after a whole sticky window, when the next step is not
+    // eligible): their n2n loads must see the increments of every sequencer warp
     WP(6);
-    if (n_acc < W * WT) wbar(BAR_W3); else __syncwarp();
+    wbar(BAR_W3);
     WP(7);
     if (sw == 0) {
       n_fast += n_acc;
