@@ -65,7 +65,7 @@ def build_host_module(force=False):
     deps = srcs + [os.path.join(CSRC, "host_api.hpp"), os.path.join(INCLUDE, "blance_b200.h"), lib_path()]
     if force or _newer(deps, out):
         cxx = os.environ.get("CXX", "g++")
-        cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden",
+        cmd = [cxx, "-O2", "-std=c++17", "-pthread", "-fPIC", "-shared", "-fvisibility=hidden",
                "-I" + INCLUDE, "-I" + CSRC, "-I" + sysconfig.get_paths()["include"], "-I" + pybind11.get_include()] + srcs + \
               ["-L" + LIBDIR, "-lblance_b200", "-Wl,-rpath,$ORIGIN/lib", "-o", out]
         _run(cmd)

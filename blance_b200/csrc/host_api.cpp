@@ -3,8 +3,12 @@
 #include "host_api.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
+#include <string_view>
+#include <thread>
 #include <unordered_set>
 
 namespace blance {
@@ -65,6 +69,113 @@ struct Interner {
     auto it = ids.find(s);
     return it == ids.end() ? -1 : it->second;
   }
+};
+
+// string_view -> dense index, open addressing; the views point into the caller's maps, which
+// outlive the call.  Built single-threaded, read from many threads.
+struct SvTable {
+  std::vector<uint32_t> slots;                  // index + 1, 0 = empty
+  std::vector<uint64_t> hashes;
+  std::vector<std::string_view> keys;
+  uint64_t mask = 0;
+  static uint64_t hash(std::string_view s) {    // FNV-1a with a final mix
+    uint64_t h = 1469598103934665603ull;
+    for (unsigned char c : s) { h ^= c; h *= 1099511628211ull; }
+    h ^= h >> 32; h *= 0x9E3779B97F4A7C15ull; h ^= h >> 29;
+    return h;
+  }
+  void init(size_t n) {
+    size_t cap = 16;
+    while (cap < n * 2 + 2) cap <<= 1;
+    slots.assign(cap, 0u);
+    mask = cap - 1;
+    hashes.reserve(n);
+    keys.reserve(n);
+  }
+  int32_t find(std::string_view s, uint64_t h) const {
+    if (slots.empty()) return -1;
+    for (uint64_t i = h & mask;; i = (i + 1) & mask) {
+      const uint32_t e = slots[i];
+      if (!e) return -1;
+      if (hashes[e - 1] == h && keys[e - 1] == s) return int32_t(e - 1);
+    }
+  }
+  int32_t insert(std::string_view s, uint64_t h) {   // the index of s, new or old
+    for (uint64_t i = h & mask;; i = (i + 1) & mask) {
+      const uint32_t e = slots[i];
+      if (!e) {
+        keys.push_back(s);
+        hashes.push_back(h);
+        slots[i] = uint32_t(keys.size());
+        return int32_t(keys.size() - 1);
+      }
+      if (hashes[e - 1] == h && keys[e - 1] == s) return int32_t(e - 1);
+    }
+  }
+};
+
+// ---- a little data parallelism for the million-partition maps (the per-partition work is independent) ----
+std::atomic<int> g_host_threads{0};             // SetHostThreads; 0 = default
+
+int max_threads() {
+  const int forced = g_host_threads.load(std::memory_order_relaxed);
+  if (forced >= 1) return forced;
+  static const int n = [] {
+    if (const char* e = std::getenv("BLANCE_HOST_THREADS")) { const int v = std::atoi(e); if (v >= 1) return std::min(v, 64); }
+    const unsigned hc = std::thread::hardware_concurrency();
+    return int(std::min(16u, std::max(1u, hc)));
+  }();
+  return n;
+}
+
+// f(begin, end, thread index); runs inline below 32 768 items
+template <class F>
+void parallel_for(size_t n, F f) {
+  const int T = max_threads();
+  if (T <= 1 || n < 32768) { if (n) f(size_t(0), n, 0); return; }
+  std::vector<std::thread> th;
+  const size_t chunk = (n + size_t(T) - 1) / size_t(T);
+  for (int t = 1; t < T; ++t) {
+    const size_t lo = std::min(n, chunk * size_t(t)), hi = std::min(n, lo + chunk);
+    if (lo < hi) th.emplace_back([=] { f(lo, hi, t); });
+  }
+  f(size_t(0), std::min(n, chunk), 0);
+  for (auto& x : th) x.join();
+}
+
+// chunk sorts in parallel, then pairwise merges
+template <class T, class Less>
+void parallel_sort(std::vector<T>& v, Less less) {
+  const int TN = max_threads();
+  if (TN <= 1 || v.size() < 65536) { std::sort(v.begin(), v.end(), less); return; }
+  int parts = 1;
+  while (parts * 2 <= TN) parts *= 2;
+  const size_t n = v.size();
+  std::vector<size_t> cut(size_t(parts) + 1);
+  for (int i = 0; i <= parts; ++i) cut[size_t(i)] = n * size_t(i) / size_t(parts);
+  {
+    std::vector<std::thread> th;
+    for (int i = 1; i < parts; ++i) th.emplace_back([&, i] { std::sort(v.begin() + long(cut[size_t(i)]), v.begin() + long(cut[size_t(i) + 1]), less); });
+    std::sort(v.begin(), v.begin() + long(cut[1]), less);
+    for (auto& x : th) x.join();
+  }
+  for (int width = 1; width < parts; width *= 2) {
+    std::vector<std::thread> th;
+    for (int i = 0; i + width < parts; i += 2 * width) {
+      const size_t lo = cut[size_t(i)], mid = cut[size_t(i + width)], hi = cut[size_t(std::min(parts, i + 2 * width))];
+      th.emplace_back([&, lo, mid, hi] { std::inplace_merge(v.begin() + long(lo), v.begin() + long(mid), v.begin() + long(hi), less); });
+    }
+    for (auto& x : th) x.join();
+  }
+}
+
+// first error raised inside a parallel region
+struct ErrorSlot {
+  std::mutex mu;
+  bool has = false;
+  std::string msg;
+  void set(const std::string& m) { std::lock_guard<std::mutex> g(mu); if (!has) { has = true; msg = m; } }
+  void rethrow() { if (has) invalid(msg); }
 };
 
 // sortStateNames (plan.go:437-474).  Go starts from random map order and its
@@ -139,6 +250,9 @@ std::unique_ptr<InternedPlan> InternPlan(const PartitionMap& prevMap, const Part
     nodes.get(n);
   }
   const int32_t N = int32_t(nodesAll.size());
+  SvTable node_tab;                              // read-only view of nodesAll for the parallel passes
+  node_tab.init(size_t(N));
+  for (const auto& n : nodesAll) node_tab.insert(n, SvTable::hash(n));
 
   // ---- states
   ip->state_names = sort_state_names(model);
@@ -173,97 +287,194 @@ std::unique_ptr<InternedPlan> InternPlan(const PartitionMap& prevMap, const Part
     for (const auto& n : by_name)
       if (top_state < 0 || model.at(n).Priority < ip->state_priority[size_t(top_state)]) top_state = state_id[n];
   }
-
-  // ---- partitions, indexed in the name order of the partition sort key
-  std::vector<NameKey> keys;
-  {
-    std::unordered_set<std::string> seen;
-    auto add = [&](const PartitionMap& m) {
-      for (const auto& kv : m) {
-        if (!kv.second.Name.empty() && kv.second.Name != kv.first)
-          invalid("Partition.Name '" + kv.second.Name + "' differs from its map key '" + kv.first + "'");
-        if (!seen.insert(kv.first).second) continue;
-        NameKey k;
-        k.raw = kv.first;
-        k.padded = kv.first;
-        long long v;
-        if (go_atoi(kv.first, &v) && v >= 0) k.padded = pad10(v);
-        keys.push_back(std::move(k));
-      }
-    };
-    add(prevMap);
-    add(partitionsToAssign);
-  }
-  std::sort(keys.begin(), keys.end(), name_key_less);
-  const int32_t PU = int32_t(keys.size());
-  ip->part_names.resize(size_t(PU));
-  std::unordered_map<std::string, int32_t> part_id;
-  part_id.reserve(size_t(PU) * 2);
-  for (int32_t p = 0; p < PU; ++p) { ip->part_names[size_t(p)] = std::move(keys[size_t(p)].raw); part_id[ip->part_names[size_t(p)]] = p; }
-
-  // ---- slot layout: a state's range holds max(constraints, longest input list)
-  std::vector<int32_t> cap(size_t(S), 0);
-  for (int32_t s = 0; s < S; ++s) cap[size_t(s)] = std::max(0, ip->state_constraints[size_t(s)]);
-  auto scan_caps = [&](const PartitionMap& m, bool must_be_model) {
-    for (const auto& kv : m)
-      for (const auto& sn : kv.second.NodesByState) {
-        auto it = state_id.find(sn.first);
-        if (it == state_id.end()) {
-          if (must_be_model)
-            invalid("partition '" + kv.first + "' has state '" + sn.first + "' that is not in the model (the reference panics, plan.go:148)");
-          continue;
-        }
-        cap[size_t(it->second)] = std::max(cap[size_t(it->second)], int32_t(deref(sn.second).size()));
-      }
+  // the model has a handful of states: comparing names beats hashing them
+  auto find_state = [&](const std::string& name) -> int32_t {
+    for (int32_t s = 0; s < S; ++s)
+      if (ip->state_names[size_t(s)].size() == name.size() && ip->state_names[size_t(s)] == name) return s;
+    return -1;
   };
-  scan_caps(prevMap, false);
-  scan_caps(partitionsToAssign, true);
-  ip->state_slot_off.assign(size_t(S) + 1, 0);
-  for (int32_t s = 0; s < S; ++s) ip->state_slot_off[size_t(s) + 1] = ip->state_slot_off[size_t(s)] + cap[size_t(s)];
-  const int32_t SL = ip->state_slot_off[size_t(S)];
 
-  // ---- rows
+  // ---- partitions, indexed in the name order of the partition sort key (plan.go:519-528, 512).
+  // The maps are walked once into pointer arrays; everything per partition after that runs in parallel.
+  using Entry = const PartitionMap::value_type*;
+  const bool same_map = &prevMap == &partitionsToAssign;
+  std::vector<Entry> pv, av;
+  auto walk = [&](const PartitionMap& m, std::vector<Entry>& out) {     // bucket ranges in parallel
+    out.resize(m.size());
+    const size_t B = m.bucket_count();
+    const int T = max_threads();
+    if (T <= 1 || m.size() < 32768) { size_t i = 0; for (const auto& kv : m) out[i++] = &kv; return; }
+    std::vector<std::vector<Entry>> part{size_t(T)};
+    parallel_for(B, [&](size_t lo, size_t hi, int t) {
+      auto& mine = part[size_t(t)];
+      mine.reserve((hi - lo) * m.size() / B + 16);
+      for (size_t b = lo; b < hi; ++b)
+        for (auto it = m.begin(b); it != m.end(b); ++it) mine.push_back(&*it);
+    });
+    size_t i = 0;
+    for (const auto& v : part) { std::copy(v.begin(), v.end(), out.begin() + long(i)); i += v.size(); }
+  };
+  walk(prevMap, pv);
+  if (!same_map) walk(partitionsToAssign, av);
+  auto check_names = [&](const std::vector<Entry>& v) {
+    ErrorSlot err;
+    parallel_for(v.size(), [&](size_t lo, size_t hi, int) {
+      for (size_t i = lo; i < hi; ++i)
+        if (!v[i]->second.Name.empty() && v[i]->second.Name != v[i]->first) {
+          err.set("Partition.Name '" + v[i]->second.Name + "' differs from its map key '" + v[i]->first + "'");
+          return;
+        }
+    });
+    err.rethrow();
+  };
+  check_names(pv);
+  check_names(av);
+  // name -> unique index (u), in first-seen order: prevMap's entries, then the new ones of partitionsToAssign
+  std::vector<uint64_t> hp(pv.size()), ha(av.size());
+  parallel_for(pv.size(), [&](size_t lo, size_t hi, int) { for (size_t i = lo; i < hi; ++i) hp[i] = SvTable::hash(pv[i]->first); });
+  parallel_for(av.size(), [&](size_t lo, size_t hi, int) { for (size_t i = lo; i < hi; ++i) ha[i] = SvTable::hash(av[i]->first); });
+  SvTable names;
+  names.init(pv.size() + av.size());
+  for (size_t i = 0; i < pv.size(); ++i) names.insert(pv[i]->first, hp[i]);        // map keys are unique: u == i
+  std::vector<int32_t> au(av.size());
+  for (size_t i = 0; i < av.size(); ++i) au[i] = names.insert(av[i]->first, ha[i]);
+  const size_t U = names.keys.size();
+  const int32_t PU = int32_t(U);
+  // sort keys: names that are small non-negative integers compare as integers ("%10d" of v < 10^10 is ten
+  // characters wide, so the padded strings order like the numbers); anything else compares as the strings do
+  struct SortKey { long long v; uint32_t u; uint32_t numeric; };
+  std::vector<SortKey> keys(U);
+  parallel_for(U, [&](size_t lo, size_t hi, int) {
+    for (size_t i = lo; i < hi; ++i) {
+      long long v = 0;
+      const std::string raw(names.keys[i]);
+      const bool num = go_atoi(raw, &v) && v >= 0 && v < 10000000000ll;
+      keys[i] = SortKey{num ? v : 0, uint32_t(i), num ? 1u : 0u};
+    }
+  });
+  auto padded_of = [&](const SortKey& k) -> std::string {
+    std::string raw(names.keys[k.u]);
+    if (k.numeric) return pad10(k.v);
+    long long v;
+    if (go_atoi(raw, &v) && v >= 0) return pad10(v);
+    return raw;
+  };
+  auto key_less = [&](const SortKey& a, const SortKey& b) {
+    if (a.numeric && b.numeric) {
+      if (a.v != b.v) return a.v < b.v;
+      return names.keys[a.u] < names.keys[b.u];
+    }
+    const std::string pa = padded_of(a), pb = padded_of(b);
+    if (pa != pb) return pa < pb;
+    return names.keys[a.u] < names.keys[b.u];
+  };
+  parallel_sort(keys, key_less);
+  std::vector<int32_t> rank(U);                 // unique index -> partition id
+  ip->part_names.resize(U);
+  parallel_for(U, [&](size_t lo, size_t hi, int) {
+    for (size_t p = lo; p < hi; ++p) { rank[keys[p].u] = int32_t(p); ip->part_names[p] = std::string(names.keys[keys[p].u]); }
+  });
+  auto part_of_prev = [&](size_t i) { return rank[i]; };
+  auto part_of_assign = [&](size_t i) { return rank[size_t(au[i])]; };
+
+  // ---- per-partition scalars
   ip->part_in_prev.assign(size_t(PU), 0);
   ip->part_in_assign.assign(size_t(PU), 0);
-  ip->prev_rows.assign(size_t(PU) * size_t(SL), BLANCE_NO_NODE);
-  ip->cur_rows.assign(size_t(PU) * size_t(SL), BLANCE_NO_NODE);
-  ip->prev_shape.assign(size_t(PU) * size_t(S), BLANCE_SHAPE_ABSENT);
-  ip->cur_shape.assign(size_t(PU) * size_t(S), BLANCE_SHAPE_ABSENT);
   ip->part_weight.assign(size_t(PU), 1);
   ip->part_has_weight.assign(size_t(PU), 0);
   ip->part_name_rank.resize(size_t(PU));
   for (int32_t p = 0; p < PU; ++p) ip->part_name_rank[size_t(p)] = p;
   if (options.PartitionWeights)
     for (const auto& kv : *options.PartitionWeights) {
-      auto it = part_id.find(kv.first);
-      if (it == part_id.end()) continue;
-      ip->part_weight[size_t(it->second)] = kv.second;
-      ip->part_has_weight[size_t(it->second)] = 1;
+      const int32_t u = names.find(kv.first, SvTable::hash(kv.first));
+      if (u < 0) continue;
+      ip->part_weight[size_t(rank[size_t(u)])] = kv.second;
+      ip->part_has_weight[size_t(rank[size_t(u)])] = 1;
     }
 
+  // ---- slot layout and rows.  A state's range holds max(constraints, longest input list).  The rows are
+  // filled in ONE pass over the maps assuming the constraints are wide enough; a longer list (rare) only
+  // records the width it needs and the pass is repeated with the right layout.
+  std::vector<int32_t> cap(size_t(S), 0);
+  for (int32_t s = 0; s < S; ++s) cap[size_t(s)] = std::max(0, ip->state_constraints[size_t(s)]);
   struct Extra { int32_t part; int32_t node; };
+  struct Unknown { size_t pos; int which; const std::string* name; };   // a row cell (or extras entry) naming a node outside nodesAll
   std::vector<Extra> extras;   // prevMap entries under non-model states (only feed tot)
-  auto fill = [&](const PartitionMap& m, std::vector<int32_t>& rows, std::vector<uint8_t>& shape,
-                  std::vector<uint8_t>& present, bool is_prev) {
-    for (const auto& kv : m) {
-      const int32_t p = part_id.at(kv.first);
-      present[size_t(p)] = 1;
-      for (const auto& sn : kv.second.NodesByState) {
-        auto it = state_id.find(sn.first);
-        if (it == state_id.end()) {
-          if (is_prev)
-            for (const auto& n : deref(sn.second)) extras.push_back({p, nodes.get(n)});
-          continue;
+  int32_t SL = 0;
+  for (int attempt = 0;; ++attempt) {
+    ip->state_slot_off.assign(size_t(S) + 1, 0);
+    for (int32_t s = 0; s < S; ++s) ip->state_slot_off[size_t(s) + 1] = ip->state_slot_off[size_t(s)] + cap[size_t(s)];
+    SL = ip->state_slot_off[size_t(S)];
+    extras.clear();
+    std::vector<int32_t> need = cap;
+    auto fill = [&](const std::vector<Entry>& v, bool from_prev, std::vector<int32_t>& rows, std::vector<uint8_t>& shape,
+                    std::vector<uint8_t>& present, bool is_prev, bool must_be_model) {
+      const int T = max_threads();
+      ErrorSlot err;
+      std::vector<std::vector<Extra>> textra{size_t(T)};
+      std::vector<std::vector<Unknown>> tunk{size_t(T)};
+      std::vector<std::vector<int32_t>> tneed(size_t(T), std::vector<int32_t>(size_t(S), 0));
+      parallel_for(v.size(), [&](size_t lo, size_t hi, int t) {
+        for (size_t i = lo; i < hi; ++i) {
+          const int32_t p = from_prev ? part_of_prev(i) : part_of_assign(i);
+          present[size_t(p)] = 1;
+          for (const auto& sn : v[i]->second.NodesByState) {
+            const int32_t s = find_state(sn.first);
+            if (s < 0) {
+              if (must_be_model) {
+                err.set("partition '" + v[i]->first + "' has state '" + sn.first + "' that is not in the model (the reference panics, plan.go:148)");
+                return;
+              }
+              if (is_prev)
+                for (const auto& n : deref(sn.second)) {
+                  const int32_t id = node_tab.find(n, SvTable::hash(n));
+                  if (id < 0) tunk[size_t(t)].push_back({textra[size_t(t)].size(), -1, &n});
+                  textra[size_t(t)].push_back({p, id});
+                }
+              continue;
+            }
+            shape[size_t(p) * size_t(S) + size_t(s)] = sn.second ? BLANCE_SHAPE_LIST : BLANCE_SHAPE_NIL;
+            const Strs& list = deref(sn.second);
+            if (int32_t(list.size()) > cap[size_t(s)]) { tneed[size_t(t)][size_t(s)] = std::max(tneed[size_t(t)][size_t(s)], int32_t(list.size())); continue; }
+            size_t pos = size_t(p) * size_t(SL) + size_t(ip->state_slot_off[size_t(s)]);
+            for (const auto& n : list) {
+              const int32_t id = node_tab.find(n, SvTable::hash(n));
+              if (id >= 0) rows[pos] = id;
+              else tunk[size_t(t)].push_back({pos, 0, &n});
+              ++pos;
+            }
+          }
         }
-        const int32_t s = it->second;
-        shape[size_t(p) * size_t(S) + size_t(s)] = sn.second ? BLANCE_SHAPE_LIST : BLANCE_SHAPE_NIL;
-        int32_t slot = ip->state_slot_off[size_t(s)];
-        for (const auto& n : deref(sn.second)) rows[size_t(p) * size_t(SL) + size_t(slot++)] = nodes.get(n);
+      });
+      err.rethrow();
+      // names outside nodesAll get their ids here, in a fixed order (thread, then position)
+      for (int t = 0; t < T; ++t) {
+        for (const auto& u : tunk[size_t(t)]) {
+          const int32_t id = nodes.get(*u.name);
+          if (u.which >= 0) rows[u.pos] = id;
+          else textra[size_t(t)][u.pos].node = id;
+        }
+        extras.insert(extras.end(), textra[size_t(t)].begin(), textra[size_t(t)].end());
+        for (int32_t s = 0; s < S; ++s) need[size_t(s)] = std::max(need[size_t(s)], tneed[size_t(t)][size_t(s)]);
       }
+    };
+    ip->prev_rows.assign(size_t(PU) * size_t(SL), BLANCE_NO_NODE);
+    ip->prev_shape.assign(size_t(PU) * size_t(S), BLANCE_SHAPE_ABSENT);
+    fill(pv, true, ip->prev_rows, ip->prev_shape, ip->part_in_prev, true, same_map);
+    if (!same_map) {
+      ip->cur_rows.assign(size_t(PU) * size_t(SL), BLANCE_NO_NODE);
+      ip->cur_shape.assign(size_t(PU) * size_t(S), BLANCE_SHAPE_ABSENT);
+      fill(av, false, ip->cur_rows, ip->cur_shape, ip->part_in_assign, false, true);
     }
-  };
-  fill(prevMap, ip->prev_rows, ip->prev_shape, ip->part_in_prev, true);
-  fill(partitionsToAssign, ip->cur_rows, ip->cur_shape, ip->part_in_assign, false);
+    if (need == cap) break;
+    if (attempt >= 1) invalid("internal: slot layout did not settle");
+    cap = need;
+  }
+  if (same_map) {
+    ip->cur_rows = ip->prev_rows;
+    ip->cur_shape = ip->prev_shape;
+    ip->part_in_assign = ip->part_in_prev;
+  }
 
   // ---- node flags (after every name that can occur has been interned)
   for (const auto& n : deref(nodesToRemove)) nodes.get(n);
@@ -398,35 +609,72 @@ PlanOutBuffers::PlanOutBuffers(const InternedPlan& ip) {
 
 PartitionMap UninternPlan(const InternedPlan& ip, const PlanOutBuffers& ob, Warnings* warnings) {
   const blance_plan_in& in = ip.in;
-  PartitionMap next;
-  next.reserve(size_t(in.n_parts));
-  for (int32_t p = 0; p < in.n_parts; ++p) {
-    if (!ip.part_in_assign[size_t(p)]) continue;                    // plan.go:326-330
-    Partition part;
-    part.Name = ip.part_names[size_t(p)];
-    const int32_t* row = ob.next_rows.data() + size_t(p) * size_t(in.n_slots);
-    for (int32_t s = 0; s < in.n_states; ++s) {
-      const uint8_t sh = ob.next_shape[size_t(p) * size_t(in.n_states) + size_t(s)];
-      if (sh == BLANCE_SHAPE_ABSENT) continue;
-      if (sh == BLANCE_SHAPE_NIL) { part.NodesByState[ip.state_names[size_t(s)]] = std::nullopt; continue; }
-      Strs list;
-      for (int32_t i = ip.state_slot_off[size_t(s)]; i < ip.state_slot_off[size_t(s) + 1] && row[i] != BLANCE_NO_NODE; ++i)
-        list.push_back(ip.node_names[size_t(row[i])]);
-      part.NodesByState[ip.state_names[size_t(s)]] = std::move(list);
+  // the assigned partitions (plan.go:326-330), built in parallel, then moved into the map
+  std::vector<int32_t> ids;
+  ids.reserve(size_t(in.n_parts));
+  for (int32_t p = 0; p < in.n_parts; ++p)
+    if (ip.part_in_assign[size_t(p)]) ids.push_back(p);
+  std::vector<Partition> parts(ids.size());
+  parallel_for(ids.size(), [&](size_t lo, size_t hi, int) {
+    for (size_t i = lo; i < hi; ++i) {
+      const int32_t p = ids[i];
+      Partition& part = parts[i];
+      part.Name = ip.part_names[size_t(p)];
+      const int32_t* row = ob.next_rows.data() + size_t(p) * size_t(in.n_slots);
+      for (int32_t s = 0; s < in.n_states; ++s) {
+        const uint8_t sh = ob.next_shape[size_t(p) * size_t(in.n_states) + size_t(s)];
+        if (sh == BLANCE_SHAPE_ABSENT) continue;
+        if (sh == BLANCE_SHAPE_NIL) { part.NodesByState[ip.state_names[size_t(s)]] = std::nullopt; continue; }
+        Strs list;
+        for (int32_t j = ip.state_slot_off[size_t(s)]; j < ip.state_slot_off[size_t(s) + 1] && row[j] != BLANCE_NO_NODE; ++j)
+          list.push_back(ip.node_names[size_t(row[j])]);
+        part.NodesByState[ip.state_names[size_t(s)]] = std::move(list);
+      }
     }
+  });
+  PartitionMap next;
+  next.reserve(ids.size());
+  for (size_t i = 0; i < ids.size(); ++i) {
+    const int32_t p = ids[i];
     if (warnings)
       for (int32_t s = 0; s < in.n_states; ++s)
         if (ob.warn[size_t(p) * size_t(in.n_states) + size_t(s)]) {
           char buf[32];                                              // plan.go:231-234
           std::snprintf(buf, sizeof buf, "%d", ip.state_constraints[size_t(s)]);
-          (*warnings)[part.Name].push_back(std::string("could not meet constraints: ") + buf +
-                                           ", stateName: " + ip.state_names[size_t(s)] +
-                                           ", partitionName: " + part.Name);
+          (*warnings)[parts[i].Name].push_back(std::string("could not meet constraints: ") + buf +
+                                               ", stateName: " + ip.state_names[size_t(s)] +
+                                               ", partitionName: " + parts[i].Name);
         }
-    next.emplace(part.Name, std::move(part));
+    std::string key = parts[i].Name;
+    next.emplace(std::move(key), std::move(parts[i]));
   }
   return next;
 }
+
+// plan.go:49-52: after any non-matching iteration the caller's maps hold the new partitions; when the loop
+// ends their content equals the returned map.  Map surgery (new keys) is serial, the deep copies are not.
+void ReplayCallerMutation(const PartitionMap& next, PartitionMap& prevMap, PartitionMap& partitionsToAssign) {
+  const bool same = &prevMap == &partitionsToAssign;
+  std::vector<const Partition*> src;
+  std::vector<Partition*> dst_prev, dst_assign;
+  src.reserve(next.size());
+  dst_prev.reserve(next.size());
+  if (!same) dst_assign.reserve(next.size());
+  for (const auto& kv : next) {
+    src.push_back(&kv.second);
+    dst_prev.push_back(&prevMap[kv.first]);
+    if (!same) dst_assign.push_back(&partitionsToAssign[kv.first]);
+  }
+  parallel_for(src.size(), [&](size_t lo, size_t hi, int) {
+    for (size_t i = lo; i < hi; ++i) {
+      *dst_prev[i] = *src[i];
+      if (!same) *dst_assign[i] = *src[i];
+    }
+  });
+}
+
+void SetHostThreads(int n) { g_host_threads.store(n < 0 ? 0 : (n > 64 ? 64 : n), std::memory_order_relaxed); }
+int HostThreads() { return max_threads(); }
 
 blance_ctx* DefaultContext() {
   static std::mutex mu;
@@ -458,15 +706,7 @@ PartitionMap PlanNextMapEx(PartitionMap& prevMap, PartitionMap& partitionsToAssi
   }
   if (ob.out.iters_run <= 0) return PartitionMap{};                  // MaxIterationsPerPlan <= 0: plan.go:32,57
   PartitionMap next = UninternPlan(*ip, ob, warnings);
-  // plan.go:49-52: after any non-matching iteration the caller's maps hold the new
-  // partitions; when the loop ends their content equals the returned map.
-  if (ob.out.iters_run >= 2 || !ob.out.converged) {
-    const bool same = &prevMap == &partitionsToAssign;
-    for (const auto& kv : next) {
-      prevMap[kv.first] = kv.second;
-      if (!same) partitionsToAssign[kv.first] = kv.second;
-    }
-  }
+  if (ob.out.iters_run >= 2 || !ob.out.converged) ReplayCallerMutation(next, prevMap, partitionsToAssign);
   return next;
 }
 

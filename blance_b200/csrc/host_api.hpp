@@ -129,6 +129,15 @@ struct PlanOutBuffers {
 // rows -> PartitionMap of the assigned partitions, plus the warning strings.
 PartitionMap UninternPlan(const InternedPlan& ip, const PlanOutBuffers& ob, Warnings* warnings);
 
+// plan.go:49-52: store the partitions of `next` into the caller's maps (they may be the same object).
+void ReplayCallerMutation(const PartitionMap& next, PartitionMap& prevMap, PartitionMap& partitionsToAssign);
+
+// The marshalling layer (InternPlan, UninternPlan, ReplayCallerMutation) splits maps of 32 768 partitions
+// or more over host threads: min(16, hardware threads) by default, BLANCE_HOST_THREADS in the environment,
+// or this call (0 = back to the default).  Results do not depend on the thread count.
+void SetHostThreads(int n);
+int HostThreads();
+
 // The process-wide context the host API runs on (created on first use).
 blance_ctx* DefaultContext();
 

@@ -237,4 +237,6 @@ PYBIND11_MODULE(_host, m) {
   });
 
   m.def("ctx_ptr", []() { return (uintptr_t)DefaultContext(); });
+  m.def("set_host_threads", [](int n) { SetHostThreads(n); });
+  m.def("host_threads", []() { return HostThreads(); });
 }
