@@ -85,3 +85,50 @@ def test_big_map_through_the_threads_equals_literal_oracle():
     assert next_map == lit["next_map"]
     assert warnings == lit["warnings"]
     assert out.iters_run == lit["iterations"]
+
+
+def test_name_order_of_a_big_map_with_mixed_names():
+    """plan.go:519-528 on 40 000 names: non-negative integers order by value ("%10d"), everything else by its
+    raw bytes, ties on the padded form by the raw name - also when the sort is split over threads."""
+    rnd = random.Random(3)
+    names = set()
+    while len(names) < P_BIG:
+        r = rnd.random()
+        v = rnd.randint(0, 99999)
+        names.add(str(v) if r < 0.5 else "%07d" % v if r < 0.6 else "+%d" % v if r < 0.65 else "-%d" % v if r < 0.7
+                  else "p%05d" % v if r < 0.9 else " %d" % v)
+    names.add(str(12345678901))          # wider than ten digits: no longer ordered like the shorter numbers
+    names.add("9999999999")
+    names = sorted(names)
+    rnd.shuffle(names)
+    nodes = ["a", "b"]
+    prev = {n: {"primary": [nodes[i & 1]]} for i, n in enumerate(names)}
+
+    def key(n):
+        try:
+            ok = n.lstrip("+-").isdigit() and n.isascii() and len(n.lstrip("+-")) == len(n) - (n[0] in "+-")
+            v = int(n) if ok else None
+        except ValueError:
+            v = None
+        return ("%10d" % v if v is not None and v >= 0 else n, n)
+
+    expect = sorted(names, key=key)
+    try:
+        for threads in (1, 6):
+            _host.set_host_threads(threads)
+            ip = _host.intern_plan(prev_map=prev, partitions_to_assign=None, nodes_all=nodes, nodes_to_remove=[],
+                                   nodes_to_add=[], model={"primary": (0, 1)})
+            assert ip.part_names == expect, threads
+    finally:
+        _host.set_host_threads(0)
+
+
+def test_errors_raised_inside_the_threads_surface():
+    kw = big_instance(9, False)
+    kw["partitions_to_assign"]["17"]["bogus"] = ["n01"]            # a state outside the model: the reference panics
+    try:
+        _host.set_host_threads(4)
+        with pytest.raises(Exception, match="not in the model"):
+            _host.intern_plan(**kw)
+    finally:
+        _host.set_host_threads(0)
