@@ -1,5 +1,5 @@
-// blance_b200/csrc/assign_pass_seq.cuh — the assign pass for rebalances: a sequencer
-// warp decides the "sticky" steps alone and wakes the whole CTA only when it must.
+// blance_b200/csrc/assign_pass_seq.cuh — the assign pass for rebalances: sequencer
+// warps decide the "sticky" steps alone and wake the whole CTA only when they must.
 //
 // Same chain as assign_pass.cuh (assignStateToPartitions + findBestNodes,
 // plan.go:98-303), same results.  The observation: in a rebalance most steps re-elect the
@@ -7,19 +7,22 @@
 // same formula (plan.go:634-689) with nodeToNodeCounts = 0 and no stickiness; all its
 // operations are monotone — and base keys only change when a count changes.  So:
 //
-//   * the CTA keeps the BL_GLIST smallest base keys of the live nodes in shared memory
-//     (glist) and a shared-memory mirror of the per-node score inputs;
-//   * the SEQUENCER warp (the service warp of the lock-step kernel) walks the steps.  For
-//     a step whose partition holds exactly k clean current nodes it computes their k exact
-//     scores from the mirror (lane q = current node q), finds the smallest cached base key
-//     among the nodes the partition could still take, and if the worst current node beats
-//     it, the reference's sort would put exactly the current nodes first: the step is
-//     decided by ONE warp with no barrier and no arg-min round (counts do not change, so
-//     the cache stays valid; only nodeToNodeCounts is bumped);
+//   * the CTA keeps the smallest base keys of the live nodes in shared memory (glist: as
+//     many as a row can block plus two, at most BL_GLIST) and a shared-memory mirror of the
+//     per-node score inputs;
+//   * the SEQUENCER warps (1 or SEQ_W_MAX per CTA) walk the steps in windows: one (step,
+//     current node) item per lane.  For a step whose partition holds exactly k clean current
+//     nodes the lanes compute the k exact scores from the mirror, find the smallest cached
+//     base key among the nodes the partition could still take, and if the worst current node
+//     beats it, the reference's sort would put exactly the current nodes first: the step is
+//     decided with no arg-min round (counts do not change, so the cache stays valid; only
+//     nodeToNodeCounts is bumped).  A window is committed up to its first step that is not
+//     sticky; two steps of a window that share (top, node) are found exactly through a small
+//     hash set in shared memory and the later one starts the next window;
 //   * any other step is handed to the compute warps through two named barriers: they run
 //     the full evaluation (the code of the lock-step kernel), update their registers, the
 //     mirror and the base keys, and report the outcome; a count change drops the cache, which
-//     is rebuilt (BL_GLIST arg-min rounds) after BL_CALM_MIN quiet steps.
+//     is rebuilt (arg-min rounds over the base keys) after up to BL_CALM_MIN quiet steps.
 //
 // The host picks this kernel per pass when the state has no hierarchy rules, k <= BL_FAST_K
 // and at least a quarter of the rows are eligible (k_pick_mode); otherwise the lock-step
