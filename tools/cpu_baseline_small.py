@@ -1,0 +1,44 @@
+"""CPU arm for BASELINE.json configs[0..2] ("time it on cfg-1/2 fully, cfg-3 fully if
+< 30 min"): the literal C++ restatement of the Go planner (oracle/literal.cpp) and the array-form oracle
+(oracle/fast.c) on the complete cfg-1, cfg-2 and cfg-3 rebalance plans, one core (the reference planner is
+single-goroutine).  No GPU.  Prints one JSON line.  Oracle code is test infrastructure: this tool only
+measures it."""
+import ctypes
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from blance_b200 import synth, tables
+from oracle_loader import fast_lib_path, literal
+
+fast = ctypes.CDLL(fast_lib_path())
+fast.oracle_fast_plan_next_map.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+L = literal()
+out = {"cores": 1, "kind": "port", "configs": {}}
+for cfg in (1, 2, 3):
+    t = synth.make_fresh(cfg)
+    if cfg != 1:                        # cfg-2/3: prev = output of a fresh plan, then remove / add nodes
+        fr = tables.PlanResult(t)
+        s0 = t.struct()
+        fast.oracle_fast_plan_next_map(ctypes.byref(s0), ctypes.byref(fr.out))
+        t = synth.make_rebalance(cfg, fr.next_rows)
+    ref = tables.PlanResult(t)
+    s = t.struct()
+    t0 = time.perf_counter()
+    fast.oracle_fast_plan_next_map(ctypes.byref(s), ctypes.byref(ref.out))
+    t_fast = time.perf_counter() - t0
+    kw = synth.to_dicts(t, cfg)
+    t0 = time.perf_counter()
+    r = L.plan_next_map_ex(**kw)
+    t_lit = time.perf_counter() - t0
+    assert r["iterations"] == ref.iters_run and int(r["steps"]) == int(ref.steps)
+    out["configs"]["cfg%d" % cfg] = {
+        "partitions": int(t.n_parts), "nodes": int(t.n_nodes), "iterations": int(ref.iters_run), "steps": int(ref.steps),
+        "literal": {"seconds": t_lit, "partitions_per_s": t.n_parts / t_lit, "findBestNodes_steps_per_s": ref.steps / t_lit},
+        "fast_oracle": {"seconds": t_fast, "partitions_per_s": t.n_parts / t_fast, "findBestNodes_steps_per_s": ref.steps / t_fast}}
+    print("cfg%d done: literal %.1f s, fast %.3f s" % (cfg, t_lit, t_fast), file=sys.stderr, flush=True)
+print(json.dumps(out))
