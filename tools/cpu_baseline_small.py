@@ -9,6 +9,8 @@ import os
 import sys
 import time
 
+import numpy as np
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -18,7 +20,7 @@ from oracle_loader import fast_lib_path, literal
 fast = ctypes.CDLL(fast_lib_path())
 fast.oracle_fast_plan_next_map.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
 L = literal()
-out = {"cores": 1, "kind": "port", "configs": {}}
+out = {"cores": 1, "kind": "port", "maps_equal": True, "configs": {}}
 for cfg in (1, 2, 3):
     t = synth.make_fresh(cfg)
     if cfg != 1:                        # cfg-2/3: prev = output of a fresh plan, then remove / add nodes
@@ -36,6 +38,20 @@ for cfg in (1, 2, 3):
     r = L.plan_next_map_ex(**kw)
     t_lit = time.perf_counter() - t0
     assert r["iterations"] == ref.iters_run and int(r["steps"]) == int(ref.steps)
+    # the two oracles agree on the complete plan (the same check tests/test_synth.py makes at reduced sizes)
+    want = synth.to_dicts(t, cfg)["partitions_to_assign"]
+    nodes = ["n%04d" % i for i in range(t.n_nodes)]
+    states = ["primary", "replica", "standby"][:t.n_states]
+    rows, shape = np.asarray(ref.next_rows).reshape(t.n_parts, -1), np.asarray(ref.next_shape).reshape(t.n_parts, -1)
+    for p in range(t.n_parts):
+        got = {}
+        for si in range(t.n_states):
+            if shape[p, si] == 0:
+                continue
+            lo, hi = int(t.state_slot_off[si]), int(t.state_slot_off[si + 1])
+            got[states[si]] = None if shape[p, si] == 1 else [nodes[x] for x in rows[p, lo:hi] if x >= 0]
+        assert got == r["next_map"][str(p)], (cfg, p)
+    assert len(r["next_map"]) == len(want)
     out["configs"]["cfg%d" % cfg] = {
         "partitions": int(t.n_parts), "nodes": int(t.n_nodes), "iterations": int(ref.iters_run), "steps": int(ref.steps),
         "literal": {"seconds": t_lit, "partitions_per_s": t.n_parts / t_lit, "findBestNodes_steps_per_s": ref.steps / t_lit},
