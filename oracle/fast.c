@@ -250,6 +250,13 @@ static void one_step(fo_t* f, int32_t p, int32_t s) {            /* plan.go:268-
 }
 
 typedef struct { uint64_t key; int32_t p; } okey_t;
+
+/* The pass loop of plan.go:268-302.  tools/spec_model.c (a design model of the product's speculative
+ * pass kernel, also test infrastructure) replaces it to check that kernel's decision rules step by
+ * step against one_step(). */
+#ifndef FO_PASS
+#define FO_PASS(f, order, lim, s) do { for (int32_t i_ = 0; i_ < (lim); i_++) one_step((f), (order)[i_].p, (s)); } while (0)
+#endif
 static int okey_cmp(const void* a, const void* b) {
   const okey_t* x = (const okey_t*)a; const okey_t* y = (const okey_t*)b;
   return x->key < y->key ? -1 : x->key > y->key ? 1 : 0;
@@ -373,7 +380,7 @@ FO_EXPORT int oracle_fast_plan_next_map_capped(const blance_plan_in* in, blance_
       memset(f.n2n, 0, sizeof(int32_t) * (size_t)(f.NU + 1) * f.N); /* plan.go:266 */
       int32_t lim = n_order;
       if (max_steps_per_pass >= 0 && max_steps_per_pass < lim) lim = (int32_t)max_steps_per_pass;
-      for (int32_t i = 0; i < lim; i++) one_step(&f, order[i].p, s);
+      FO_PASS(&f, order, lim, s);
     }
     out->iters_run = it + 1;
 
