@@ -107,7 +107,7 @@ class _PlanOut(ctypes.Structure):
 
 
 _CAPI = None
-EXPORTS = ("blance_ctx_create", "blance_ctx_destroy", "blance_last_error", "blance_version", "blance_ctx_kernel_launches", "blance_plan_next_map",
+EXPORTS = ("blance_ctx_create", "blance_ctx_create_multi", "blance_ctx_device_count", "blance_ctx_destroy", "blance_last_error", "blance_version", "blance_ctx_kernel_launches", "blance_plan_next_map",
            "blance_plan_next_map_batch", "blance_plan_upload", "blance_plan_run", "blance_plan_fetch", "blance_plan_free", "blance_plan_timing",
            "blance_calc_partition_moves")
 
@@ -120,6 +120,8 @@ def capi():
         lib = ctypes.CDLL(os.environ.get("BLANCE_B200_LIB", _build.lib_path()))   # override: instrumented builds
         vp, i32 = ctypes.c_void_p, ctypes.c_int32
         lib.blance_ctx_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int]
+        lib.blance_ctx_create_multi.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int), ctypes.c_int]
+        lib.blance_ctx_device_count.argtypes = [vp]
         lib.blance_ctx_destroy.argtypes = [vp]
         lib.blance_ctx_destroy.restype = None
         lib.blance_last_error.argtypes = [vp]

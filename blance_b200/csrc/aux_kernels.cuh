@@ -204,25 +204,72 @@ __global__ void k_gather_stream(DPool pool, int s, long long n_parts_total) {
     dst[D.SLP + 6] = n_cur;
     dst[D.SLP + 7] = clean ? 1 : 0;
     if (clean && n_cur == D.state_constraints[s]) atomicAdd(&pool.insts[pool.part_inst[g]].n_elig, 1);
+    if (clean && n_cur <= D.state_constraints[s]) atomicAdd(&pool.insts[pool.part_inst[g]].n_clean, 1);
+  }
+}
+
+// ---- the all-sticky hypothesis of the speculative pass (assign_pass_spec.cuh) -----------------------------
+// If every eligible step (clean row, exactly k current nodes) kept its nodes, step i would find
+// nodeToNodeCounts[top][c] = the number of EARLIER eligible steps of the pass with the same (top, c) pair.
+// k_pair_keys emits one (pair, item) per eligible step and current node, a stable radix sort groups the pairs
+// (items of a pair stay in step order), k_pair_rank turns the position inside the group into qstat[step][q].
+__global__ void k_pair_keys(DPool pool, int s, long long n_parts_total, int inst_shift) {
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n_parts_total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int inst = pool.part_inst[g];
+    const DInst& D = pool.insts[inst];
+    unsigned long long key[4] = {~0ull, ~0ull, ~0ull, ~0ull};
+    const long long i = g - D.part_off;
+    if (D.active && s < D.S && D.pass_mode == 2 && i < D.n_assign) {
+      const int REC = D.SLP + 8, k = D.state_constraints[s];
+      const int32_t* rec = pool.stream + D.stream_off + i * REC;
+      if (rec[D.SLP + 7] != 0 && rec[D.SLP + 6] == k) {
+        const unsigned long long hi = ((unsigned long long)(uint32_t)inst << inst_shift) | ((unsigned long long)(uint32_t)rec[D.SLP + 2] << 13);
+        for (int q = 0; q < k && q < 4; ++q) key[q] = hi | (unsigned long long)(uint32_t)rec[D.state_slot_off[s] + q];
+      }
+    }
+    for (int q = 0; q < 4; ++q) {
+      pool.pair_keys_alt[4 * g + q] = key[q];
+      pool.pair_vals_alt[4 * g + q] = (uint32_t)(4 * g + q);
+      pool.qstat[4 * g + q] = 0;
+    }
+  }
+}
+
+__global__ void k_pair_rank(DPool pool, long long n_items) {
+  for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n_items; x += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long key = pool.pair_keys[x];
+    if (key == ~0ull) continue;
+    long long lo = 0, hi = x;                  // first position holding `key` (keys are sorted)
+    while (lo < hi) {
+      const long long mid = (lo + hi) >> 1;
+      if (pool.pair_keys[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    pool.qstat[pool.pair_vals[x]] = (int32_t)(x - lo);
   }
 }
 
 // Which kernel runs the pass of state s for each instance (one thread per instance): the sequencer
 // kernel pays off when many rows can be decided by the sticky test; it needs k <= 4, no hierarchy
 // rules for the state, and a node mirror that fits in shared memory.
-__global__ void k_pick_mode(DPool pool, int s, int n_inst, int seq_allowed) {
+__global__ void k_pick_mode(DPool pool, int s, int n_inst, int seq_allowed, int spec_allowed, int spec_max_n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_inst) return;
   DInst& D = pool.insts[i];
   int mode = 0;
   if (D.active && s < D.S && D.state_constraints[s] > 0) {
     const bool rules = D.has_hier_rules && D.rule_off[s + 1] > D.rule_off[s];
-    if (seq_allowed && D.engine == BLANCE_ENGINE_AUTO && !rules && D.state_constraints[s] <= 4 && D.N <= 4096 && D.SLP <= 8 && D.n_assign >= 64 &&
-        4ll * D.n_elig >= (long long)D.n_assign)
-      mode = 1;
+    const bool shape_ok = !rules && D.state_constraints[s] <= 4 && D.SLP <= 8 && D.n_assign >= 64 && 4ll * D.n_elig >= (long long)D.n_assign;
+    if (seq_allowed && (D.engine == BLANCE_ENGINE_AUTO || D.engine == BLANCE_ENGINE_SEQUENCER) && shape_ok && D.N <= 4096) mode = 1;
+    // the speculative kernel resolves clean rows with at most k current nodes on its own; anything else costs a
+    // full team evaluation, so it wants nearly all rows clean
+    if (spec_allowed && D.engine == BLANCE_ENGINE_AUTO && shape_ok && D.N <= spec_max_n &&
+        64ll * D.n_clean >= 63ll * (long long)D.n_assign)
+      mode = 2;
   }
   D.pass_mode = mode;
   D.n_elig = 0;
+  D.n_clean = 0;
 }
 
 // After the pass: rebuild every partition's row from the step's outcome (plan.go:290-301), in
@@ -279,7 +326,8 @@ __global__ void k_compare(DPool pool, long long n_parts_total) {
     DInst& D = pool.insts[pool.part_inst[g]];
     const uint8_t f = pool.pflags[g];
     if (!D.active || !(f & PF_IN_ASSIGN)) continue;
-    bool same = (f & PF_IN_PREV) && ((pool.pmeta[g] & 0xFFFFu) == (pool.prev_meta[g] & 0xFFFFu));
+    // (a prevMap entry with keys outside the model never equals the new partition: reflect.DeepEqual, plan.go:38)
+    bool same = (f & PF_IN_PREV) && !(f & PF_PREV_EXTRA) && ((pool.pmeta[g] & 0xFFFFu) == (pool.prev_meta[g] & 0xFFFFu));
     if (same) {
       const int32_t* a = pool.rows + D.rows_off + (g - D.part_off) * D.SLP;
       const int32_t* b = pool.prev_rows + D.rows_off + (g - D.part_off) * D.SLP;
@@ -300,7 +348,7 @@ __global__ void k_commit(DPool pool, long long n_parts_total) {
     int32_t* b = pool.prev_rows + D.rows_off + (g - D.part_off) * D.SLP;
     for (int i = 0; i < D.SLP; ++i) b[i] = a[i];
     pool.prev_meta[g] = pool.pmeta[g] & 0xFFFFu;
-    pool.pflags[g] = f | PF_IN_PREV;
+    pool.pflags[g] = (uint8_t)((f | PF_IN_PREV) & ~PF_PREV_EXTRA);
   }
 }
 

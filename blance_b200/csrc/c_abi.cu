@@ -9,6 +9,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -16,6 +17,7 @@
 
 #include "assign_pass.cuh"
 #include "assign_pass_seq.cuh"
+#include "assign_pass_spec.cuh"
 #include "aux_kernels.cuh"
 #include "blance_b200.h"
 #include "device_types.cuh"
@@ -28,6 +30,7 @@ static std::string g_create_error;
 // (function, device) pair, not to a blance_ctx, and must only ever be raised.
 static std::mutex g_seq_dyn_mu;
 static size_t g_seq_dyn[64][4][4];   // [device][NPT index][K - 1]
+static size_t g_spec_dyn[64][4];     // [device][K - 1], k_assign_pass_spec
 
 struct blance_ctx {
   int device = 0;
@@ -42,6 +45,9 @@ struct blance_ctx {
   int* d_any_active = nullptr;
   int* h_any_active = nullptr;       // pinned
   long long launches = 0;            // kernels of this library launched so far
+  void* h_stage = nullptr;           // pinned staging of a batch (kept between calls, grow-only)
+  size_t h_stage_bytes = 0;
+  std::vector<blance_ctx*> children; // blance_ctx_create_multi: one single-device context per GPU
 };
 
 #define CK(call)                                                                           \
@@ -62,7 +68,14 @@ static int fail(blance_ctx* ctx, int st, const std::string& msg) {
 
 extern "C" int blance_version(void) { return 100; }
 
-extern "C" int64_t blance_ctx_kernel_launches(const blance_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int64_t blance_ctx_kernel_launches(const blance_ctx* ctx) {
+  if (!ctx) return 0;
+  long long n = ctx->launches;
+  for (const blance_ctx* c : ctx->children) n += c->launches;
+  return n;
+}
+
+extern "C" int blance_ctx_device_count(const blance_ctx* ctx) { return !ctx ? 0 : ctx->children.empty() ? 1 : (int)ctx->children.size(); }
 
 extern "C" const char* blance_last_error(const blance_ctx* ctx) {
   return ctx ? ctx->err.c_str() : g_create_error.c_str();
@@ -108,8 +121,40 @@ extern "C" int blance_ctx_create(blance_ctx** out, int device_id) {
   return BLANCE_OK;
 }
 
+// One context over several GPUs of the node (blance_ctx_create(gpu_ids, n_gpus)).  A batch
+// (blance_plan_next_map_batch) is sharded instance i -> device i mod n, one host thread per device, no collective:
+// plan instances are independent.  Everything else runs on the first device.
+extern "C" int blance_ctx_create_multi(blance_ctx** out, const int* device_ids, int n_devices) {
+  if (!out) return fail(nullptr, BLANCE_ERR_INVALID_ARG, "blance_ctx_create_multi: out is NULL");
+  *out = nullptr;
+  if (!device_ids || n_devices <= 0) return fail(nullptr, BLANCE_ERR_INVALID_ARG, "blance_ctx_create_multi: no devices given");
+  for (int a = 0; a < n_devices; ++a)
+    for (int b = 0; b < a; ++b)
+      if (device_ids[a] == device_ids[b]) return fail(nullptr, BLANCE_ERR_INVALID_ARG, "blance_ctx_create_multi: a device is listed twice");
+  blance_ctx* parent = new blance_ctx();
+  for (int a = 0; a < n_devices; ++a) {
+    blance_ctx* c = nullptr;
+    const int st = blance_ctx_create(&c, device_ids[a]);
+    if (st != BLANCE_OK) {
+      for (blance_ctx* k : parent->children) blance_ctx_destroy(k);
+      delete parent;
+      return st;                       // g_create_error already says why
+    }
+    parent->children.push_back(c);
+  }
+  parent->device = parent->children[0]->device;
+  parent->sm_count = parent->children[0]->sm_count;
+  *out = parent;
+  return BLANCE_OK;
+}
+
 extern "C" void blance_ctx_destroy(blance_ctx* ctx) {
   if (!ctx) return;
+  if (!ctx->children.empty()) {
+    for (blance_ctx* c : ctx->children) blance_ctx_destroy(c);
+    delete ctx;
+    return;
+  }
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (auto ev : ctx->events) cudaEventDestroy(ev);
@@ -117,6 +162,7 @@ extern "C" void blance_ctx_destroy(blance_ctx* ctx) {
   if (ctx->cub_tmp) cudaFree(ctx->cub_tmp);
   if (ctx->d_any_active) cudaFree(ctx->d_any_active);
   if (ctx->h_any_active) cudaFreeHost(ctx->h_any_active);
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -129,7 +175,8 @@ struct blance_plan {
   std::vector<DInst> h_insts;          // initial descriptors (dynamic fields at their start values)
   std::vector<long long> raw_rows_off, raw_shape_off;   // caller-layout offsets per instance
   long long PT = 0, RT = 0, NT = 0, NUT = 0, CT = 0, N2T = 0, MT = 0, RRT = 0, RST = 0, ST = 0;
-  int max_N = 0, max_S = 0;
+  int max_N = 0, max_S = 0, max_NU = 0;
+  int pair_inst_shift = 0, pair_end_bit = 64;   // key layout of the (top, node) pair sort (k_pair_keys)
   bool any_state_active[BL_S_MAX] = {};
   void* arena = nullptr;               // one device allocation, carved below
   size_t arena_bytes = 0;
@@ -192,7 +239,7 @@ static int validate(blance_ctx* ctx, const blance_plan_in* in, int idx) {
       if ((in->rule_off[s + 1] - in->rule_off[s]) * std::max(0, in->state_constraints[s]) > BL_PICK_MAX)
         return bad("rules x constraints > 32 for one state", BLANCE_ERR_UNSUPPORTED);
   }
-  if (in->engine != BLANCE_ENGINE_AUTO && in->engine != BLANCE_ENGINE_LOCKSTEP) return bad("unknown engine", BLANCE_ERR_UNSUPPORTED);
+  if (in->engine != BLANCE_ENGINE_AUTO && in->engine != BLANCE_ENGINE_LOCKSTEP && in->engine != BLANCE_ENGINE_SEQUENCER) return bad("unknown engine", BLANCE_ERR_UNSUPPORTED);
   if (in->booster_kind != BLANCE_BOOSTER_NONE && in->booster_kind != BLANCE_BOOSTER_CBGT_MAX)
     return bad("unknown booster_kind", BLANCE_ERR_UNSUPPORTED);
   return BLANCE_OK;
@@ -204,8 +251,7 @@ static void plan_release(blance_plan* pl, blance_ctx* ctx = nullptr) {
     if (ctx) cudaFreeAsync(pl->arena, ctx->stream);     // back to the pool (stream ordered)
     else cudaFree(pl->arena);
   }
-  if (pl->h_stage) cudaFreeHost(pl->h_stage);
-  delete pl;
+  delete pl;                         // (the pinned staging buffer belongs to the context)
 }
 
 static int grid_for(const blance_ctx* ctx, long long n, int block) {
@@ -272,11 +318,18 @@ static int upload(blance_ctx* ctx, int n, const blance_plan_in* ins, blance_plan
     pl->CT += (long long)D.S * D.N; pl->N2T += (long long)(D.NU + 1) * D.N;
     pl->MT += (long long)D.n_rules * (D.NU + 1) * D.HW;
     pl->RRT += (long long)D.PU * D.SL; pl->RST += (long long)D.PU * D.S;
-    pl->max_N = std::max(pl->max_N, D.N); pl->max_S = std::max(pl->max_S, D.S);
+    pl->max_N = std::max(pl->max_N, D.N); pl->max_S = std::max(pl->max_S, D.S); pl->max_NU = std::max(pl->max_NU, D.NU);
   }
   seg_off[n] = (int)pl->PT;
   pl->raw_rows_off[n] = pl->RRT; pl->raw_shape_off[n] = pl->RST;
-  if (pl->PT >= (1LL << 31)) { plan_release(pl, ctx); return fail(ctx, BLANCE_ERR_UNSUPPORTED, "2^31 or more partitions in one batch"); }
+  if (pl->PT >= (1LL << 29)) { plan_release(pl, ctx); return fail(ctx, BLANCE_ERR_UNSUPPORTED, "2^29 or more partitions in one batch"); }
+  {
+    int top_bits = 1, inst_bits = 1;
+    while ((1ll << top_bits) < (long long)pl->max_NU + 2) ++top_bits;
+    while ((1ll << inst_bits) < (long long)n + 1) ++inst_bits;
+    pl->pair_inst_shift = 13 + top_bits;
+    pl->pair_end_bit = pl->pair_inst_shift + inst_bits;
+  }
 
   // ---- carve one device arena ------------------------------------------------------------
   struct Slice { void** ptr; size_t bytes; };
@@ -298,6 +351,9 @@ static int upload(blance_ctx* ctx, int n, const blance_plan_in* ins, blance_plan
   SL_(c_rm, uint8_t, NUT); SL_(c_ad, uint8_t, NUT); SL_(c_nw, int32_t, NT); SL_(c_hw, uint8_t, NT);
   SL_(c_ef, int32_t, NT); SL_(c_er, int32_t, NT);
   SL_(P.counts, int32_t, CT); SL_(P.n2n, int32_t, N2T); SL_(c_mask, uint32_t, MT);
+  SL_(P.n2n_dev, int32_t, N2T); SL_(P.qstat, int32_t, 4 * PT);
+  SL_(P.pair_keys, unsigned long long, 4 * PT); SL_(P.pair_keys_alt, unsigned long long, 4 * PT);
+  SL_(P.pair_vals, uint32_t, 4 * PT); SL_(P.pair_vals_alt, uint32_t, 4 * PT);
   SL_(P.insts, DInst, (size_t)n);
   SL_(pl->raw_a, int32_t, RRT); SL_(pl->raw_b, int32_t, RRT); SL_(pl->rawsh_a, uint8_t, RST); SL_(pl->rawsh_b, uint8_t, RST);
   SL_(pl->d_raw_rows_off, long long, (size_t)n + 1); SL_(pl->d_raw_shape_off, long long, (size_t)n + 1);
@@ -333,7 +389,7 @@ static int upload(blance_ctx* ctx, int n, const blance_plan_in* ins, blance_plan
     const DInst& D = pl->h_insts[0];
     v_flags.resize((size_t)D.PU + 1);
     for (int p = 0; p < D.PU; ++p)
-      v_flags[p] = (uint8_t)((in.part_in_prev[p] ? PF_IN_PREV : 0) | (in.part_in_assign[p] ? PF_IN_ASSIGN : 0) |
+      v_flags[p] = (uint8_t)((in.part_in_prev[p] ? PF_IN_PREV : 0) | ((in.part_in_prev[p] & 2) ? PF_PREV_EXTRA : 0) | (in.part_in_assign[p] ? PF_IN_ASSIGN : 0) |
                              (in.part_has_weight[p] ? PF_HAS_WEIGHT : 0));
     h_cur = in.cur_rows; h_prev = in.prev_rows; h_csh = in.cur_shape; h_psh = in.prev_shape;
     h_flags = v_flags.data(); h_pw = in.part_weight; h_rank = in.part_name_rank;     // h_inst stays NULL: all zero
@@ -344,11 +400,17 @@ static int upload(blance_ctx* ctx, int n, const blance_plan_in* ins, blance_plan
   const size_t stage_bytes = align_up(sizeof(int32_t) * RRT, 256) * 2 + align_up(RST, 256) * 2 + align_up(PT, 256) +
                              align_up(sizeof(int32_t) * PT, 256) * 3 + align_up(NUT, 256) * 2 +
                              align_up(sizeof(int32_t) * NT, 256) * 3 + align_up(NT, 256) + align_up(sizeof(uint32_t) * MT, 256);
-  e = cudaMallocHost(&pl->h_stage, stage_bytes);
-  if (e != cudaSuccess) {
-    plan_release(pl, ctx);
-    return fail(ctx, BLANCE_ERR_NOMEM, std::string("cudaMallocHost of the staging buffer failed: ") + cudaGetErrorString(e));
+  if (stage_bytes > ctx->h_stage_bytes) {          // grow-only, kept by the context between calls
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    ctx->h_stage = nullptr; ctx->h_stage_bytes = 0;
+    e = cudaMallocHost(&ctx->h_stage, stage_bytes + stage_bytes / 4);
+    if (e != cudaSuccess) {
+      plan_release(pl, ctx);
+      return fail(ctx, BLANCE_ERR_NOMEM, std::string("cudaMallocHost of the staging buffer failed: ") + cudaGetErrorString(e));
+    }
+    ctx->h_stage_bytes = stage_bytes + stage_bytes / 4;
   }
+  pl->h_stage = ctx->h_stage;
   pl->h_stage_bytes = stage_bytes;
   char* hp = (char*)pl->h_stage;
   auto carve = [&](size_t bytes) { char* r = hp; hp += align_up(bytes, 256); return r; };
@@ -367,7 +429,7 @@ static int upload(blance_ctx* ctx, int n, const blance_plan_in* ins, blance_plan
   int32_t* s_er = (int32_t*)carve(sizeof(int32_t) * NT);
   uint8_t* s_hw = (uint8_t*)carve(NT);
   uint32_t* s_mask = (uint32_t*)carve(sizeof(uint32_t) * MT);
-  for (int i = 0; i < n; ++i) {
+  auto stage_one = [&](int i) {
     const blance_plan_in& in = ins[i];
     const DInst& D = pl->h_insts[i];
     const size_t rr = (size_t)D.PU * D.SL, rs = (size_t)D.PU * D.S;
@@ -376,7 +438,7 @@ static int upload(blance_ctx* ctx, int n, const blance_plan_in* ins, blance_plan
     if (rs) { std::memcpy(s_csh + pl->raw_shape_off[i], in.cur_shape, rs); std::memcpy(s_psh + pl->raw_shape_off[i], in.prev_shape, rs); }
     for (int p = 0; p < D.PU; ++p) {
       const size_t g = (size_t)D.part_off + p;
-      s_flags[g] = (uint8_t)((in.part_in_prev[p] ? PF_IN_PREV : 0) | (in.part_in_assign[p] ? PF_IN_ASSIGN : 0) |
+      s_flags[g] = (uint8_t)((in.part_in_prev[p] ? PF_IN_PREV : 0) | ((in.part_in_prev[p] & 2) ? PF_PREV_EXTRA : 0) | (in.part_in_assign[p] ? PF_IN_ASSIGN : 0) |
                              (in.part_has_weight[p] ? PF_HAS_WEIGHT : 0));
       s_pw[g] = in.part_weight[p];
       s_rank[g] = in.part_name_rank[p];
@@ -391,6 +453,17 @@ static int upload(blance_ctx* ctx, int n, const blance_plan_in* ins, blance_plan
     }
     const size_t mw = (size_t)D.n_rules * (D.NU + 1) * D.HW;
     if (mw) std::memcpy(s_mask + D.mask_off, in.ie_mask, sizeof(uint32_t) * mw);
+  };
+  {
+    // instances are staged by a few host threads (a 1 024-instance fan-out is ~1 M partitions of flag packing)
+    int T = (int)std::min<long long>(8, std::max<long long>(1, pl->PT / 65536));
+    T = std::min(T, std::max(1, (int)std::thread::hardware_concurrency()));
+    if (T <= 1) { for (int i = 0; i < n; ++i) stage_one(i); }
+    else {
+      std::vector<std::thread> th;
+      for (int t = 0; t < T; ++t) th.emplace_back([&, t]() { for (int i = t; i < n; i += T) stage_one(i); });
+      for (auto& x : th) x.join();
+    }
   }
   h_cur = s_cur; h_prev = s_prev; h_csh = s_csh; h_psh = s_psh; h_flags = s_flags; h_pw = s_pw; h_rank = s_rank;
   h_inst = s_inst; h_rm = s_rm; h_ad = s_ad; h_nw = s_nw; h_hw = s_hw; h_ef = s_ef; h_er = s_er; h_mask = s_mask;
@@ -431,6 +504,11 @@ static int upload(blance_ctx* ctx, int n, const blance_plan_in* ins, blance_plan
   cub::DeviceSegmentedRadixSort::SortPairs(nullptr, need2, P.keys_alt, P.keys, P.order_alt, P.order, (int)pl->PT, n,
                                            pl->d_seg_off, pl->d_seg_off + 1, 0, 64, st);
   need = std::max(need, need2);
+  {
+    size_t need3 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, need3, P.pair_keys_alt, P.pair_keys, P.pair_vals_alt, P.pair_vals, (int)(4 * pl->PT), 0, 64, st);
+    need = std::max(need, need3);
+  }
   if (need > ctx->cub_tmp_bytes) {
     if (ctx->cub_tmp) cudaFree(ctx->cub_tmp);
     ctx->cub_tmp = nullptr; ctx->cub_tmp_bytes = 0;
@@ -485,6 +563,21 @@ static cudaError_t launch_pass_seq(size_t* configured, const DPool& P, int n_ins
   if (e == cudaSuccess && (kmask & 8u)) e = launch_pass_seq_k<NPT, 3, MAXT>(configured + 2, P, n_inst, TC, W, s, dyn, st);
   if (e == cudaSuccess && (kmask & 16u)) e = launch_pass_seq_k<NPT, 4, MAXT>(configured + 3, P, n_inst, TC, W, s, dyn, st);
   return e;
+}
+
+// the speculative variant, one instantiation per constraint count K (CTAs of other modes / other K exit at once)
+template <int K>
+static cudaError_t launch_pass_spec_k(size_t* configured, const DPool& P, int n_inst, int nw, int sw, unsigned idle_mask, int s, size_t dyn, cudaStream_t st) {
+  {
+    std::lock_guard<std::mutex> g(g_seq_dyn_mu);
+    if (dyn > *configured) {
+      cudaError_t e = cudaFuncSetAttribute(k_assign_pass_spec<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+      if (e != cudaSuccess) return e;
+      *configured = dyn;
+    }
+  }
+  k_assign_pass_spec<K><<<n_inst, 32 * nw, dyn, st>>>(P, s, sw, idle_mask);
+  return cudaSuccess;
 }
 
 static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
@@ -557,7 +650,28 @@ static int run(blance_ctx* ctx, blance_plan* pl) {
         CK(cub::DeviceSegmentedRadixSort::SortPairs(ctx->cub_tmp, tmp, P.keys_alt, P.keys, P.order_alt, P.order, (int)pl->PT,
                                                     n, pl->d_seg_off, pl->d_seg_off + 1, 0, 64, st));
       k_gather_stream<<<grid, blk, 0, st>>>(P, s, pl->PT);
-      k_pick_mode<<<(n + 127) / 128, 128, 0, st>>>(P, s, n, (npt <= 8 && !getenv("BLANCE_NO_SEQ")) ? 1 : 0);
+      unsigned kmask = 0;
+      for (int i = 0; i < n; ++i) { const int kk = pl->h_insts[i].S > s ? pl->h_insts[i].state_constraints[s] : 0; if (kk >= 1 && kk <= 4) kmask |= 1u << kk; }
+      // speculative kernel: 9 scout warps + the leader (warps 4 and 8 stay away from the leader's scheduler) when the
+      // GPU has SMs to spare, 3 scouts per CTA for wide batches
+      const bool spec_wide = 2 * n <= ctx->sm_count;
+      const int spec_nw = spec_wide ? 12 : 4, spec_sw = spec_wide ? 9 : 3;
+      const unsigned spec_idle = spec_wide ? ((1u << 4) | (1u << 8)) : 0u;
+      const int spec_max_n = std::min(2048, 32 * spec_sw * SP_NPTS);
+      bool any_auto = false;
+      for (int i = 0; i < n; ++i) any_auto |= pl->h_insts[i].engine == BLANCE_ENGINE_AUTO;
+      const bool spec_allowed = any_auto && kmask != 0 && pl->pair_end_bit <= 62 && !getenv("BLANCE_NO_SPEC");
+      k_pick_mode<<<(n + 127) / 128, 128, 0, st>>>(P, s, n, (npt <= 8 && !getenv("BLANCE_NO_SEQ")) ? 1 : 0, spec_allowed ? 1 : 0, spec_max_n);
+      if (spec_allowed) {
+        // the all-sticky hypothesis counts (qstat) of the instances that picked the speculative kernel
+        k_pair_keys<<<grid, blk, 0, st>>>(P, s, pl->PT, pl->pair_inst_shift);
+        size_t tmp2 = ctx->cub_tmp_bytes;
+        CK(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp, tmp2, P.pair_keys_alt, P.pair_keys, P.pair_vals_alt, P.pair_vals,
+                                           (int)(4 * pl->PT), 0, pl->pair_end_bit + 1, st));
+        k_pair_rank<<<grid_for(ctx, 4 * pl->PT, blk), blk, 0, st>>>(P, 4 * pl->PT);
+        CK(cudaMemsetAsync(P.n2n_dev, 0, sizeof(int32_t) * (size_t)(pl->N2T + 1), st));
+        ctx->launches += 2;
+      }
       CK(cudaMemsetAsync(P.n2n, 0, sizeof(int32_t) * (size_t)(pl->N2T + 1), st));     // plan.go:266
       cudaEvent_t e0 = get_event(ctx, n_ev), e1 = get_event(ctx, n_ev + 1);
       if (e0 && e1 && n_ev < 256) CK(cudaEventRecord(e0, st));
@@ -567,8 +681,6 @@ static int run(blance_ctx* ctx, blance_plan* pl) {
       else if (npt == 8) launch_pass<8, 544>(P, n, T + 32, s, any_hier, st);
       else launch_pass<16, 544>(P, n, T + 32, s, any_hier, st);
       cudaError_t se = cudaSuccess;
-      unsigned kmask = 0;
-      for (int i = 0; i < n; ++i) { const int kk = pl->h_insts[i].S > s ? pl->h_insts[i].state_constraints[s] : 0; if (kk >= 1 && kk <= 4) kmask |= 1u << kk; }
       // sequencer warps per CTA: wide windows when the GPU has SMs to spare, one warp for wide batches
       int seq_w = (2 * n <= ctx->sm_count) ? SEQ_W_MAX : 1;
       if (const char* ev = getenv("BLANCE_SEQ_W")) { const int v = atoi(ev); if (v >= 1 && v <= SEQ_W_MAX) seq_w = v; }   // experiments
@@ -579,6 +691,17 @@ static int run(blance_ctx* ctx, blance_plan* pl) {
       CK(se);
       CK(cudaGetLastError());
       ctx->launches += 1 + (npt <= 8 ? __builtin_popcount(kmask) : 0);   // k_pick_mode + the sequencer kernel(s)
+      if (spec_allowed) {
+        const size_t sdyn = spec_dyn_smem_bytes(std::min(pl->max_N, spec_max_n), spec_sw);
+        size_t* cfgd = g_spec_dyn[ctx->device & 63];
+        cudaError_t pe = cudaSuccess;
+        if (pe == cudaSuccess && (kmask & 2u)) pe = launch_pass_spec_k<1>(cfgd + 0, P, n, spec_nw, spec_sw, spec_idle, s, sdyn, st);
+        if (pe == cudaSuccess && (kmask & 4u)) pe = launch_pass_spec_k<2>(cfgd + 1, P, n, spec_nw, spec_sw, spec_idle, s, sdyn, st);
+        if (pe == cudaSuccess && (kmask & 8u)) pe = launch_pass_spec_k<3>(cfgd + 2, P, n, spec_nw, spec_sw, spec_idle, s, sdyn, st);
+        if (pe == cudaSuccess && (kmask & 16u)) pe = launch_pass_spec_k<4>(cfgd + 3, P, n, spec_nw, spec_sw, spec_idle, s, sdyn, st);
+        CK(pe);
+        ctx->launches += __builtin_popcount(kmask);
+      }
       CK(cudaGetLastError());
       if (e0 && e1 && n_ev < 256) { CK(cudaEventRecord(e1, st)); n_ev += 2; }
       pl->pass_launches++;
@@ -640,6 +763,13 @@ static int fetch(blance_ctx* ctx, blance_plan* pl, blance_plan_out* outs) {
   std::vector<DInst> fin(n);
   CK(cudaMemcpyAsync(fin.data(), pl->pool.insts, sizeof(DInst) * (size_t)n, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  if (getenv("BLANCE_SPEC_STATS"))
+    for (int i = 0; i < n && i < 4; ++i)
+      std::fprintf(stderr, "[blance] inst %d: steps %lld accepted %lld | resolved by the leader %lld (stale results %lld) movers %lld team %lld rebuilds %lld waits %lld\n",
+                   i, fin[i].steps, fin[i].fast_steps, fin[i].spec_resolved, fin[i].spec_stale, fin[i].spec_movers, fin[i].spec_team,
+                   fin[i].spec_rebuilds, fin[i].spec_waits),
+      std::fprintf(stderr, "[blance]   leader cycles: scans %lld | waits %lld | resolves %lld | mover updates %lld | team %lld | passes total %lld\n",
+                   fin[i].spec_cyc[0], fin[i].spec_cyc[1], fin[i].spec_cyc[2], fin[i].spec_cyc[3], fin[i].spec_cyc[4], fin[i].spec_cyc[5]);
   for (int i = 0; i < n; ++i) {
     const DInst& D = pl->h_insts[i];
     blance_plan_out& o = outs[i];
@@ -661,6 +791,7 @@ static int fetch(blance_ctx* ctx, blance_plan* pl, blance_plan_out* outs) {
 }
 
 extern "C" int blance_plan_upload(blance_ctx* ctx, const blance_plan_in* in, blance_plan** plan) {
+  if (ctx && !ctx->children.empty()) ctx = ctx->children[0];
   if (!ctx) return fail(nullptr, BLANCE_ERR_INVALID_ARG, "ctx is NULL");
   if (!plan) return fail(ctx, BLANCE_ERR_INVALID_ARG, "plan is NULL");
   std::lock_guard<std::mutex> g(ctx->mu);
@@ -668,12 +799,14 @@ extern "C" int blance_plan_upload(blance_ctx* ctx, const blance_plan_in* in, bla
 }
 
 extern "C" int blance_plan_run(blance_ctx* ctx, blance_plan* plan) {
+  if (ctx && !ctx->children.empty()) ctx = ctx->children[0];
   if (!ctx || !plan) return fail(ctx, BLANCE_ERR_INVALID_ARG, "ctx or plan is NULL");
   std::lock_guard<std::mutex> g(ctx->mu);
   return run(ctx, plan);
 }
 
 extern "C" int blance_plan_fetch(blance_ctx* ctx, blance_plan* plan, blance_plan_out* out) {
+  if (ctx && !ctx->children.empty()) ctx = ctx->children[0];
   if (!ctx || !plan || !out) return fail(ctx, BLANCE_ERR_INVALID_ARG, "ctx, plan or out is NULL");
   std::lock_guard<std::mutex> g(ctx->mu);
   return fetch(ctx, plan, out);
@@ -689,13 +822,12 @@ extern "C" int blance_plan_timing(const blance_plan* plan, float* kernel_ms, flo
 
 extern "C" void blance_plan_free(blance_ctx* ctx, blance_plan* plan) {
   if (!plan) return;
+  if (ctx && !ctx->children.empty()) ctx = ctx->children[0];
   if (ctx) { std::lock_guard<std::mutex> g(ctx->mu); cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); plan_release(plan, ctx); }
   else plan_release(plan);
 }
 
-static int plan_batch(blance_ctx* ctx, int32_t n, const blance_plan_in* in, blance_plan_out* out) {
-  if (!ctx) return fail(nullptr, BLANCE_ERR_INVALID_ARG, "ctx is NULL");
-  if (!in || !out) return fail(ctx, BLANCE_ERR_INVALID_ARG, "in or out is NULL");
+static int plan_batch_one(blance_ctx* ctx, int32_t n, const blance_plan_in* in, blance_plan_out* out) {
   std::lock_guard<std::mutex> g(ctx->mu);
   CK(cudaSetDevice(ctx->device));
   CK(cudaEventRecord(ctx->ev[0], ctx->stream));
@@ -715,6 +847,37 @@ static int plan_batch(blance_ctx* ctx, int32_t n, const blance_plan_in* in, blan
   return st;
 }
 
+static int plan_batch(blance_ctx* ctx, int32_t n, const blance_plan_in* in, blance_plan_out* out) {
+  if (!ctx) return fail(nullptr, BLANCE_ERR_INVALID_ARG, "ctx is NULL");
+  if (!in || !out) return fail(ctx, BLANCE_ERR_INVALID_ARG, "in or out is NULL");
+  if (ctx->children.empty()) return plan_batch_one(ctx, n, in, out);
+  if (n <= 0) return fail(ctx, BLANCE_ERR_INVALID_ARG, "batch size must be positive");
+  // ---- several GPUs: instance i -> device i mod G, one host thread per device, no collective -------------------
+  const int G = (int)std::min<size_t>(ctx->children.size(), (size_t)n);
+  if (G == 1) {
+    const int st = plan_batch_one(ctx->children[0], n, in, out);
+    if (st != BLANCE_OK) ctx->err = ctx->children[0]->err;
+    return st;
+  }
+  std::vector<std::vector<blance_plan_in>> ins((size_t)G);
+  std::vector<std::vector<blance_plan_out>> outs((size_t)G);
+  for (int i = 0; i < n; ++i) { ins[(size_t)(i % G)].push_back(in[i]); outs[(size_t)(i % G)].push_back(out[i]); }
+  std::vector<int> status((size_t)G, BLANCE_OK);
+  std::vector<std::thread> th;
+  for (int d = 0; d < G; ++d)
+    th.emplace_back([&, d]() {
+      status[(size_t)d] = plan_batch_one(ctx->children[(size_t)d], (int32_t)ins[(size_t)d].size(), ins[(size_t)d].data(), outs[(size_t)d].data());
+    });
+  for (auto& t : th) t.join();
+  for (int d = 0; d < G; ++d)
+    if (status[(size_t)d] != BLANCE_OK) {
+      ctx->err = "device " + std::to_string(ctx->children[(size_t)d]->device) + ": " + ctx->children[(size_t)d]->err;
+      return status[(size_t)d];
+    }
+  for (int i = 0; i < n; ++i) out[i] = outs[(size_t)(i % G)][(size_t)(i / G)];
+  return BLANCE_OK;
+}
+
 extern "C" int blance_plan_next_map(blance_ctx* ctx, const blance_plan_in* in, blance_plan_out* out) {
   return plan_batch(ctx, 1, in, out);
 }
@@ -728,6 +891,13 @@ extern "C" int blance_calc_partition_moves(blance_ctx* ctx, int32_t n_parts, int
                                            const int32_t* end_rows, int32_t favor_min_nodes, int32_t max_ops,
                                            int32_t* op_node, uint8_t* op_state, uint8_t* op_kind, int32_t* op_count) {
   if (!ctx) return fail(nullptr, BLANCE_ERR_INVALID_ARG, "ctx is NULL");
+  if (!ctx->children.empty()) {
+    blance_ctx* c0 = ctx->children[0];
+    const int st = blance_calc_partition_moves(c0, n_parts, n_states, n_visit_states, state_slot_off, beg_rows, end_rows,
+                                               favor_min_nodes, max_ops, op_node, op_state, op_kind, op_count);
+    if (st != BLANCE_OK) ctx->err = c0->err;
+    return st;
+  }
   if (n_parts < 0 || n_states < 0 || n_visit_states < 0 || n_visit_states > n_states || !state_slot_off || max_ops < 0)
     return fail(ctx, BLANCE_ERR_INVALID_ARG, "blance_calc_partition_moves: bad sizes");
   if (n_parts == 0) return BLANCE_OK;

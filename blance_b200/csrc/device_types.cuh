@@ -15,6 +15,10 @@
 //                                                (row | meta, w_p, top, partition | stickiness)
 //   counts             int32 [S_i][N_i]          stateNodeCounts (plan.go:92-94)
 //   n2n                int32 [NU_i+1][N_i]       nodeToNodeCounts (plan.go:266), row NU = ""
+//   n2n_dev            int32 [NU_i+1][N_i]       speculative pass: n2n minus the all-sticky hypothesis
+//   qstat              int32 [sum PU_i][4]       speculative pass: per step and current node, the number of
+//                                                earlier eligible steps with the same (top, node) pair
+//   pair_keys / vals   uint64 / uint32 [4 sum PU_i] (x2) the pair sort behind qstat
 //   ie_mask            uint32[R_i][NU_i+1][HW_i] hierarchy include/exclude bit sets
 #pragma once
 
@@ -26,7 +30,8 @@
 #define BL_PICK_MAX 32    // hierarchy picks per step (rules x constraints)
 #define BL_RING 8         // step-record ring depth in shared memory (records i .. i+3 live, i+4 in flight)
 
-enum : uint8_t { PF_IN_PREV = 1, PF_IN_ASSIGN = 2, PF_HAS_WEIGHT = 4 };
+enum : uint8_t { PF_IN_PREV = 1, PF_IN_ASSIGN = 2, PF_HAS_WEIGHT = 4,
+                 PF_PREV_EXTRA = 8 };   // the prevMap entry has keys outside the model (until plan.go:49-52 replaces it)
 
 struct DInst {
   // static scalars
@@ -44,11 +49,15 @@ struct DInst {
   int32_t add_is_nil;      // nodesToAdd == nil (plan.go:554)
   int32_t use_rest;        // extra_tot_rest instead of extra_tot_first
   int32_t active, converged, iters_run, mismatch;
-  int32_t pass_mode;       // kernel of the current pass: 0 lock-step (assign_pass.cuh), 1 sequencer (assign_pass_seq.cuh)
+  int32_t pass_mode;       // kernel of the current pass: 0 lock-step (assign_pass.cuh), 1 sequencer (assign_pass_seq.cuh),
+                           // 2 speculative (assign_pass_spec.cuh)
   int32_t n_elig;          // rows of the current pass that hold exactly k clean current nodes (k_gather_stream)
-  int32_t pad_;
+  int32_t n_clean;         // rows of the current pass that are clean and hold at most k current nodes
   long long steps;
-  long long fast_steps;    // steps decided by the sequencer alone
+  long long fast_steps;    // steps decided without a full evaluation (sequencer windows / accepted scout results)
+  // counters of the speculative kernel (whole plan)
+  long long spec_resolved, spec_movers, spec_team, spec_rebuilds, spec_waits, spec_stale;
+  long long spec_cyc[6];   // leader cycles: group scans, waits, resolves, mover updates, team calls, whole passes
 };
 
 struct DPool {
@@ -66,6 +75,11 @@ struct DPool {
   const int32_t* extra_first; const int32_t* extra_rest;      // [N]
   // tables
   int32_t* counts; int32_t* n2n; const uint32_t* ie_mask;
+  // speculative pass: n2n's deviation from the all-sticky hypothesis, the per-step hypothesis counts
+  // (qstat[step][4]) and the (top, node) pair sort that produces them
+  int32_t* n2n_dev; int32_t* qstat;
+  unsigned long long* pair_keys; unsigned long long* pair_keys_alt;
+  uint32_t* pair_vals; uint32_t* pair_vals_alt;
   DInst* insts;
 };
 

@@ -417,7 +417,7 @@ std::unique_ptr<InternedPlan> InternPlan(const PartitionMap& prevMap, const Part
       parallel_for(v.size(), [&](size_t lo, size_t hi, int t) {
         for (size_t i = lo; i < hi; ++i) {
           const int32_t p = from_prev ? part_of_prev(i) : part_of_assign(i);
-          present[size_t(p)] = 1;
+          present[size_t(p)] |= 1;
           for (const auto& sn : v[i]->second.NodesByState) {
             const int32_t s = find_state(sn.first);
             if (s < 0) {
@@ -425,6 +425,7 @@ std::unique_ptr<InternedPlan> InternPlan(const PartitionMap& prevMap, const Part
                 err.set("partition '" + v[i]->first + "' has state '" + sn.first + "' that is not in the model (the reference panics, plan.go:148)");
                 return;
               }
+              if (is_prev) present[size_t(p)] = 3;        // a key outside the model: never DeepEqual (plan.go:38)
               if (is_prev)
                 for (const auto& n : deref(sn.second)) {
                   const int32_t id = node_tab.find(n, SvTable::hash(n));

@@ -107,12 +107,20 @@ class PlanResult:
 class Context:
     """A blance_ctx* (one per process/GPU)."""
 
-    def __init__(self, device_id=-1):
+    def __init__(self, device_id=-1, device_ids=None):
+        """device_ids (a list) creates a multi-GPU context: batches are sharded over those devices."""
         self.lib = api.capi()
         self.ptr = ctypes.c_void_p()
-        st = self.lib.blance_ctx_create(ctypes.byref(self.ptr), device_id)
+        if device_ids is not None:
+            arr = (ctypes.c_int * len(device_ids))(*device_ids)
+            st = self.lib.blance_ctx_create_multi(ctypes.byref(self.ptr), arr, len(device_ids))
+        else:
+            st = self.lib.blance_ctx_create(ctypes.byref(self.ptr), device_id)
         if st != 0:
             raise api.BlanceError("blance_ctx_create failed (%d): %s" % (st, self.lib.blance_last_error(None).decode()))
+
+    def device_count(self):
+        return int(self.lib.blance_ctx_device_count(self.ptr))
 
     def _check(self, st, what):
         if st != 0:
@@ -130,6 +138,22 @@ class Context:
         results = results or [PlanResult(t) for t in tables_list]
         ins = (api.PlanIn * n)(*[t.struct() for t in tables_list])
         outs = (api.PlanOut * n)(*[r.out for r in results])
+        self._check(self.lib.blance_plan_next_map_batch(self.ptr, n, ins, outs), "blance_plan_next_map_batch")
+        for r, o in zip(results, outs):
+            r.out = o
+        return results
+
+    def prepare_batch(self, tables_list, results=None):
+        """Builds the blance_plan_in / blance_plan_out arrays of a batch once; run_batch() is then only the
+        C call (what a compiled host would do per request)."""
+        n = len(tables_list)
+        results = results or [PlanResult(t) for t in tables_list]
+        ins = (api.PlanIn * n)(*[t.struct() for t in tables_list])
+        outs = (api.PlanOut * n)(*[r.out for r in results])
+        return n, ins, outs, results, tables_list
+
+    def run_batch(self, prepared):
+        n, ins, outs, results, _ = prepared
         self._check(self.lib.blance_plan_next_map_batch(self.ptr, n, ins, outs), "blance_plan_next_map_batch")
         for r, o in zip(results, outs):
             r.out = o

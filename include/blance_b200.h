@@ -48,7 +48,7 @@ enum blance_status {
   BLANCE_ERR_INVALID_ARG = -1,   /* malformed tables (the reference would panic or misbehave) */
   BLANCE_ERR_UNSUPPORTED = -2,   /* e.g. a CustomNodeSorter (plan.go:580) cannot cross the ABI */
   BLANCE_ERR_CUDA = -3,          /* no device / launch or runtime failure */
-  BLANCE_ERR_NCCL = -4,
+  /* -4 is retired (it named a collective library; the data path has no collective) */
   BLANCE_ERR_NOMEM = -5
 };
 
@@ -57,11 +57,12 @@ enum blance_status {
 enum blance_booster { BLANCE_BOOSTER_NONE = 0, BLANCE_BOOSTER_CBGT_MAX = 1 };
 
 /* Which kernel runs the sequential greedy chain of a state pass.  AUTO picks per
- * pass: the sequencer kernel when many rows are sticky, the lock-step kernel otherwise.  Results are
- * identical either way. */
+ * pass: the speculative kernel (scout warps + one committing leader) when nearly all rows are clean and many
+ * are sticky, the lock-step kernel otherwise.  Results are identical whichever kernel runs. */
 enum blance_engine {
   BLANCE_ENGINE_AUTO = 0,
-  BLANCE_ENGINE_LOCKSTEP = 1      /* never use the sequencer kernel */
+  BLANCE_ENGINE_LOCKSTEP = 1,     /* the lock-step kernel only */
+  BLANCE_ENGINE_SEQUENCER = 2     /* round 1's sequencer-window kernel where it applies, else lock-step */
 };
 
 typedef struct blance_ctx blance_ctx;   /* owns the device, streams, scratch buffers */
@@ -69,6 +70,11 @@ typedef struct blance_ctx blance_ctx;   /* owns the device, streams, scratch buf
 /* device_id < 0: current device.  Replaces nothing in the reference (it has no
  * handle); the Go shim keeps one per process/GPU. */
 int blance_ctx_create(blance_ctx** out, int device_id);
+/* One context over several GPUs of the node.  blance_plan_next_map_batch() shards its instances over them
+ * (instance i -> device_ids[i mod n_devices], one host thread per device; plan instances are independent, so
+ * there is no collective in the data path); every other entry point runs on device_ids[0]. */
+int blance_ctx_create_multi(blance_ctx** out, const int* device_ids, int n_devices);
+int blance_ctx_device_count(const blance_ctx* ctx);
 void blance_ctx_destroy(blance_ctx* ctx);
 const char* blance_last_error(const blance_ctx* ctx);   /* ctx may be NULL: last create error */
 int blance_version(void);
@@ -106,7 +112,9 @@ typedef struct blance_plan_in {
   const uint8_t* node_has_weight;       /* key present */
 
   /* per partition, [n_parts] */
-  const uint8_t* part_in_prev;          /* key of prevMap */
+  const uint8_t* part_in_prev;          /* bit 0: key of prevMap; bit 1 (value 3): that entry also holds state names
+                                         * that are not in the model - reflect.DeepEqual (plan.go:38) then never matches
+                                         * it, so the first iteration cannot converge */
   const uint8_t* part_in_assign;        /* key of partitionsToAssign */
   const int32_t* part_weight;           /* PartitionWeights[p] */
   const uint8_t* part_has_weight;       /* key present */
@@ -145,10 +153,11 @@ typedef struct blance_plan_out {
   int32_t iters_run;       /* inner plans executed (plan.go:32) */
   int32_t converged;       /* 1 if the last compare of plan.go:36-42 matched */
   int64_t steps;           /* findBestNodes calls executed over all iterations */
-  float device_ms;         /* GPU time of the whole call (events on the ctx stream), H2D/D2H included */
+  float device_ms;         /* GPU time of the whole call (events on the ctx stream), H2D/D2H included; 0 after
+                            * blance_plan_fetch (the resident path has no single call to time) */
   float kernel_ms;         /* GPU time with tables resident (between the copies) */
   float pass_ms;           /* time inside the sequential assign passes only */
-  int64_t sticky_steps;    /* of `steps`: decided by the sequencer's sticky test without a full evaluation */
+  int64_t sticky_steps;    /* of `steps`: accepted scout results / sequencer-window steps (no full evaluation) */
 } blance_plan_out;
 
 /* Host buffers in, host buffers out.  If prevMap and partitionsToAssign must be
@@ -157,7 +166,8 @@ typedef struct blance_plan_out {
 int blance_plan_next_map(blance_ctx* ctx, const blance_plan_in* in, blance_plan_out* out);
 
 /* n independent instances (multi-tenant rebalance fan-out); instance i uses
- * in[i] / out[i].  All instances run concurrently on the device. */
+ * in[i] / out[i].  All instances of a device run concurrently (one CTA each per pass); a multi-device
+ * context spreads them over its GPUs. */
 int blance_plan_next_map_batch(blance_ctx* ctx, int32_t n, const blance_plan_in* in, blance_plan_out* out);
 
 /* Device-resident variant used by benchmarks and by callers that chain plans:

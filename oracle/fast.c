@@ -388,7 +388,7 @@ FO_EXPORT int oracle_fast_plan_next_map_capped(const blance_plan_in* in, blance_
     int match = 1;
     for (int32_t p = 0; p < f.PU && match; p++) {
       if (!in->part_in_assign[p]) continue;
-      if (!f.in_prev[p]) { match = 0; break; }
+      if (!f.in_prev[p] || (f.in_prev[p] & 2)) { match = 0; break; }   /* bit 1: prevMap entry with non-model keys */
       if (memcmp(f.shape + (size_t)p * f.S, f.prev_shape + (size_t)p * f.S, (size_t)f.S)) { match = 0; break; }
       if (memcmp(f.rows + (size_t)p * f.SL, f.prev_rows + (size_t)p * f.SL, sizeof(int32_t) * (size_t)f.SL)) match = 0;
     }

@@ -86,4 +86,14 @@ def random_instance(seed, max_nodes=10, max_parts=20):
         if rnd.random() < 0.85:
             kw["hierarchy_rules"] = {s: [(rnd.randint(0, 3), rnd.randint(0, 3)) for _ in range(rnd.randint(0, 2))]
                                      for s in states if rnd.random() < 0.7}
+    # a prevMap entry of an ASSIGNED partition with a key outside the model: reflect.DeepEqual (plan.go:38) can
+    # never match it, so the first iteration cannot converge (drawn from a separate stream: older seeds keep
+    # their instances)
+    rnd2 = random.Random(seed * 7919 + 13)
+    if assign is not None and prev and rnd2.random() < 0.25:
+        both = [n for n in names if n in prev and n in assign]
+        if both:
+            n = rnd2.choice(both)
+            prev[n] = dict(prev[n])
+            prev[n]["dead"] = rnd2.choice([[], None, [rnd2.choice(nodes)]])
     return kw

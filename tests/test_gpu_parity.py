@@ -161,7 +161,7 @@ def test_random_midsize_tables_gpu_vs_oracle(ctx, chunk):
     for seed in range(chunk * 8, (chunk + 1) * 8):
         t = random_tables(seed)
         ref = oracle_tables(t)
-        for engine in (0, 1):
+        for engine in (0, 1, 2):
             t.engine = engine
             got = ctx.plan_next_map(t)
             assert np.array_equal(got.next_rows, ref.next_rows), (seed, engine)
