@@ -96,10 +96,33 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+WORKLOAD = "cfg4: PlanNextMapEx 1048576 partitions x 1024 nodes, k=(1,2), node+partition weights, stickiness, -16/+16 nodes"
+# Every partition takes exactly one findBestNodes step per state pass (plan.go:268) and the cluster does not converge
+# (tests/test_gpu_parity.py::test_cfg4_full_size_bit_exact pins iters_run == MaxIterationsPerPlan == 10 on the GPU and on
+# the oracle), so a complete plan is 2 passes x 10 iterations = 20 steps per partition.
+STEPS_PER_PARTITION = 2 * 10
+
+
+def literal_slices(parts, n_slices, slice_steps):
+    """The reference-equivalent CPU path (oracle/literal.cpp: string hash maps + comparison sort, statement for
+    statement plan.go) on the REAL maps of the workload: the cfg-4 PartitionMap of `parts` partitions is built once,
+    one inner plan (plan.go:60) starts on it, and the greedy chain of its two state passes is timed in slices of
+    `slice_steps` consecutive findBestNodes steps.  Returns the per-slice seconds."""
+    from oracle_loader import literal
+    from blance_b200 import synth                      # table builder only: loads no native product code
+    L = literal()
+    t = synth.make_rebalance(CFG, P=parts)
+    kw = synth.to_dicts(t, CFG)
+    kw["partitions_to_assign"] = None                  # the same map object twice, as blance's callers do
+    kw["max_iterations"] = 1
+    per_pass = ((n_slices + 1) // 2) * slice_steps
+    r = L.plan_next_map_ex(**kw, max_steps_per_pass=per_pass, slice_steps=slice_steps)
+    return list(r["slice_seconds"])[:n_slices]
+
+
 def cpu_literal_sample(parts, seed_offset=0):
-    """The literal oracle on a cfg-4-shaped cluster with `parts` partitions x 1024 nodes,
-    one inner plan (per-step cost does not depend on the partition count, only the two
-    O(P log P) partition sorts do).  Returns (findBestNodes steps, seconds)."""
+    """The literal oracle on a cfg-4-shaped cluster with `parts` partitions x 1024 nodes, one inner plan.
+    Returns (findBestNodes steps, seconds)."""
     from oracle_loader import literal
     from blance_b200 import synth
     L = literal()
@@ -136,47 +159,37 @@ def ncu_traffic(steps_per_launch):
         return None
 
 
-def workload_facts():
-    """Deterministic properties of the benchmark cluster (measured by the GPU arm and the array-form
-    oracle, committed as profiles/workload_cfg4.json) so the CPU arm can convert findBestNodes steps/s to
-    partitions/s: the cluster does not converge, the loop of plan.go:32 runs all 10 iterations, i.e.
-    2 state passes x 10 = 20 steps per partition."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "workload_cfg4.json")) as f:
-            return json.load(f)
-    except Exception:
-        return {"workload": "cfg4", "n_parts": 1048576, "n_nodes": 1024, "iterations": 10,
-                "findBestNodes_steps": 20971520, "steps_per_partition": 20.0}
+def shared_config(n_parts, n_nodes):
+    """The part of `config` both arms print identically."""
+    return {"workload": WORKLOAD if (n_parts, n_nodes) == (1048576, 1024) else
+            "cfg4 shape at %d partitions x %d nodes (debug size, not the headline)" % (n_parts, n_nodes),
+            "n_parts": n_parts, "n_nodes": n_nodes, "steps_per_partition": float(STEPS_PER_PARTITION)}
 
 
 def run_reference(args, rank, world):
+    """--impl reference: the reference's own algorithm on the host cores.  One bench step = one slice of
+    `--cpu-slice-steps` consecutive findBestNodes steps of the real workload's first inner plan."""
     if rank != 0:
         return
-    facts = workload_facts()
-    spp = facts["steps_per_partition"] if facts else None
-    sample_parts = args.cpu_sample_parts
-    times, steps = [], 0
-    for i in range(args.warmup + args.steps):
-        st, sec = cpu_literal_sample(sample_parts, seed_offset=i)
-        if i >= args.warmup:
-            times.append(sec)
-            steps += st
-    total = sum(times)
-    steps_per_s = steps / total
-    value = steps_per_s / spp if spp else None
+    parts = args.parts or 1048576
+    n = args.warmup + args.steps
+    secs = literal_slices(parts, n, args.cpu_slice_steps)
+    timed = secs[args.warmup:]
+    total = sum(timed)
+    steps_per_s = args.cpu_slice_steps * len(timed) / total
+    value = steps_per_s / STEPS_PER_PARTITION
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, len(timed)), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64 score / int32 tables", "data": "synthetic",
-        "config": {"workload": "cfg4: PlanNextMapEx 1048576 partitions x 1024 nodes, k=(1,2), node+partition weights, "
-                               "stickiness, -16/+16 nodes", "steps_per_partition": spp,
-                   "parallelism": "1 host core (the reference planner is single-goroutine)"},
+        "config": shared_config(parts, 1024),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
                          "findBestNodes_steps_per_s": steps_per_s,
-                         "sample": "literal C++ restatement of the Go planner (oracle/literal.cpp); each step = one inner plan "
-                                   "of a %d-partition x 1024-node cluster of the cfg4 shape; partitions/s = measured "
-                                   "findBestNodes steps/s / %s steps per partition of the full workload (per-step cost is "
-                                   "flat in the partition count)" % (sample_parts, spp)},
+                         "sample": "oracle/literal.cpp (C++ restatement of plan.go with the reference's string maps and "
+                                   "comparison sort; Go itself cannot be built in this image) on the real %d x 1024 cfg-4 maps: "
+                                   "%d slices of %d consecutive findBestNodes steps of the first inner plan (both state passes), "
+                                   "timed inside the pass loop; partitions/s = steps/s / %d steps per partition; 1 core because "
+                                   "the reference planner is single-goroutine" % (parts, len(timed), args.cpu_slice_steps, STEPS_PER_PARTITION)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -190,6 +203,7 @@ def main():
     ap.add_argument("--impl", default="blance_b200")
     ap.add_argument("--parts", type=int, default=None, help="override the partition count (debug only; invalidates the headline)")
     ap.add_argument("--cpu-sample-parts", type=int, default=1024)
+    ap.add_argument("--cpu-slice-steps", type=int, default=256, help="findBestNodes steps per reference-arm bench step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -10,18 +10,26 @@ reference (PlanNextMapEx, PlanNextMap, CalcPartitionMoves, ...).
 There is no CPU fallback: importing works anywhere the shared objects were built,
 but every compute call raises BlanceError without a CUDA device.
 """
+import importlib
 import os
 
 from . import build as _build
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
-if not (os.path.exists(_build.lib_path()) and os.path.exists(_build.host_module_path())):
-    _build.build_all()
-
-from . import _host  # noqa: E402
-from .api import (BOOSTER_CBGT_MAX, BOOSTER_NONE, BlanceError, CalcPartitionMoves, CalcPartitionMovesMap,  # noqa: E402,F401
-                  NodeStateOp, PlanNextMap, PlanNextMapEx, PlanNextMapOptions, capi)
-
+_API_NAMES = ("BOOSTER_CBGT_MAX", "BOOSTER_NONE", "BlanceError", "CalcPartitionMoves", "CalcPartitionMovesMap",
+              "NodeStateOp", "PlanNextMap", "PlanNextMapEx", "PlanNextMapOptions", "capi")
 __all__ = ["PlanNextMap", "PlanNextMapEx", "PlanNextMapOptions", "CalcPartitionMoves", "CalcPartitionMovesMap",
            "NodeStateOp", "BlanceError", "BOOSTER_NONE", "BOOSTER_CBGT_MAX", "capi"]
+
+
+def __getattr__(name):
+    """The native pieces (_host*.so, libblance_b200.so) load on first use of the API, not at import: the table
+    builders `blance_b200.synth` / `blance_b200.tables` stay importable by processes that must not map the
+    product's libraries (bench.py's CPU reference arm)."""
+    if name == "_host" or name == "api" or name in _API_NAMES:
+        if not (os.path.exists(_build.lib_path()) and os.path.exists(_build.host_module_path())):
+            _build.build_all()
+        mod = importlib.import_module("." + ("_host" if name == "_host" else "api"), __name__)
+        return mod if name in ("_host", "api") else getattr(mod, name)
+    raise AttributeError("module %r has no attribute %r" % (__name__, name))

@@ -203,6 +203,7 @@ __global__ void k_gather_stream(DPool pool, int s, long long n_parts_total) {
     }
     dst[D.SLP + 6] = n_cur;
     dst[D.SLP + 7] = clean ? 1 : 0;
+    pool.srank[g] = 0;
     if (clean && n_cur == D.state_constraints[s]) atomicAdd(&pool.insts[pool.part_inst[g]].n_elig, 1);
     if (clean && n_cur <= D.state_constraints[s]) atomicAdd(&pool.insts[pool.part_inst[g]].n_clean, 1);
   }
@@ -284,11 +285,18 @@ __global__ void k_scatter_stream(DPool pool, int s, long long n_parts_total) {
     if (i >= D.n_assign) continue;
     const int REC = D.SLP + 8, k = D.state_constraints[s];
     const int32_t* in = pool.stream + D.stream_off + i * REC;
-    const int32_t* out = pool.ostream + D.stream_off + i * REC;
+    const int32_t* out_rec = pool.ostream + D.stream_off + i * REC;
     const int32_t p = in[D.SLP + 3];
     const uint32_t meta = (uint32_t)in[D.SLP];
-    const int n_chosen = out[k];
     const int lo_s = D.state_slot_off[s], hi_s = D.state_slot_off[s + 1];
+    // a step the speculative kernel accepted as sticky keeps its k current nodes, in (score, position) order:
+    // srank = 0x80 | rank of current node q in bits 2q..2q+1
+    const uint32_t sr = pool.srank[g];
+    int32_t sticky_out[4];
+    if (sr & 0x80u)
+      for (int q = 0; q < k && q < 4; ++q) sticky_out[(sr >> (2 * q)) & 3u] = in[lo_s + q];
+    const int32_t* out = (sr & 0x80u) ? sticky_out : out_rec;
+    const int n_chosen = (sr & 0x80u) ? k : out_rec[k];
     int32_t* row = pool.rows + D.rows_off + (long long)p * D.SLP;
     uint32_t nmeta = meta;
     bool have_higher_key = false;
@@ -414,6 +422,53 @@ __global__ void k_calc_moves(int32_t n_parts, int32_t n_states, int32_t n_visit,
     }
     op_count[p] = cnt;
   }
+}
+
+// ---- move lists for the orchestrator: CSR compaction and one round of findAvailableMovesUnlocked -----------------
+__global__ void k_moves_compact(int32_t n_parts, int32_t max_ops, const long long* __restrict__ op_off,
+                                const int32_t* __restrict__ op_count, const int32_t* __restrict__ in_node,
+                                const uint8_t* __restrict__ in_state, const uint8_t* __restrict__ in_kind,
+                                int32_t* __restrict__ out_node, uint8_t* __restrict__ out_state, uint8_t* __restrict__ out_kind) {
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n_parts; p += (long long)gridDim.x * blockDim.x) {
+    const long long o = op_off[p];
+    for (int j = 0; j < op_count[p]; ++j) {
+      out_node[o + j] = in_node[p * max_ops + j];
+      out_state[o + j] = in_state[p * max_ops + j];
+      out_kind[o + j] = in_kind[p * max_ops + j];
+    }
+  }
+}
+
+__device__ __forceinline__ int move_op_weight(int kind) {           // MoveOpWeight, orchestrate.go:189-194
+  return kind == BLANCE_OP_PROMOTE ? 1 : kind == BLANCE_OP_DEMOTE ? 2 : kind == BLANCE_OP_ADD ? 3 : 4;
+}
+
+// per partition: the node of its next move (orchestrate.go:755-757) as a sort key; per node: how many, and the
+// lowest (MoveOpWeight, partition) (orchestrate.go:177-186 with a fixed tie order)
+__global__ void k_moves_next(int32_t n_parts, int32_t n_node_ids, const long long* __restrict__ op_off,
+                             const int32_t* __restrict__ op_node, const uint8_t* __restrict__ op_kind,
+                             const int32_t* __restrict__ next, uint32_t* __restrict__ key, int32_t* __restrict__ val,
+                             int32_t* __restrict__ node_cnt, unsigned long long* __restrict__ node_best) {
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n_parts; p += (long long)gridDim.x * blockDim.x) {
+    uint32_t k = 0xFFFFFFFFu;
+    const long long n_ops = op_off[p + 1] - op_off[p];
+    const int32_t nx = next[p];
+    if (nx >= 0 && nx < n_ops) {
+      const int32_t node = op_node[op_off[p] + nx];
+      if (node >= 0 && node < n_node_ids) {
+        k = (uint32_t)node;
+        atomicAdd(&node_cnt[node], 1);
+        atomicMin(&node_best[node], ((unsigned long long)move_op_weight(op_kind[op_off[p] + nx]) << 32) | (uint32_t)p);
+      }
+    }
+    key[p] = k;
+    val[p] = (int32_t)p;
+  }
+}
+
+__global__ void k_moves_best(int32_t n_node_ids, const unsigned long long* __restrict__ node_best, int32_t* __restrict__ best_part) {
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < n_node_ids; n += gridDim.x * blockDim.x)
+    best_part[n] = node_best[n] == ~0ull ? -1 : (int32_t)(node_best[n] & 0xFFFFFFFFull);
 }
 
 }  // namespace blance_dev

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <cub/device/device_segmented_radix_sort.cuh>
 
 #include "assign_pass.cuh"
@@ -351,7 +352,7 @@ static int upload(blance_ctx* ctx, int n, const blance_plan_in* ins, blance_plan
   SL_(c_rm, uint8_t, NUT); SL_(c_ad, uint8_t, NUT); SL_(c_nw, int32_t, NT); SL_(c_hw, uint8_t, NT);
   SL_(c_ef, int32_t, NT); SL_(c_er, int32_t, NT);
   SL_(P.counts, int32_t, CT); SL_(P.n2n, int32_t, N2T); SL_(c_mask, uint32_t, MT);
-  SL_(P.n2n_dev, int32_t, N2T); SL_(P.qstat, int32_t, 4 * PT);
+  SL_(P.n2n_dev, int32_t, N2T); SL_(P.qstat, int32_t, 4 * PT); SL_(P.srank, uint8_t, PT);
   SL_(P.pair_keys, unsigned long long, 4 * PT); SL_(P.pair_keys_alt, unsigned long long, 4 * PT);
   SL_(P.pair_vals, uint32_t, 4 * PT); SL_(P.pair_vals_alt, uint32_t, 4 * PT);
   SL_(P.insts, DInst, (size_t)n);
@@ -567,7 +568,7 @@ static cudaError_t launch_pass_seq(size_t* configured, const DPool& P, int n_ins
 
 // the speculative variant, one instantiation per constraint count K (CTAs of other modes / other K exit at once)
 template <int K>
-static cudaError_t launch_pass_spec_k(size_t* configured, const DPool& P, int n_inst, int nw, int sw, unsigned idle_mask, int s, size_t dyn, cudaStream_t st) {
+static cudaError_t launch_pass_spec_k(size_t* configured, const DPool& P, int n_inst, int nw, int sw, unsigned idle_mask, int shift, int s, size_t dyn, cudaStream_t st) {
   {
     std::lock_guard<std::mutex> g(g_seq_dyn_mu);
     if (dyn > *configured) {
@@ -576,7 +577,7 @@ static cudaError_t launch_pass_spec_k(size_t* configured, const DPool& P, int n_
       *configured = dyn;
     }
   }
-  k_assign_pass_spec<K><<<n_inst, 32 * nw, dyn, st>>>(P, s, sw, idle_mask);
+  k_assign_pass_spec<K><<<n_inst, 32 * nw, dyn, st>>>(P, s, sw, idle_mask, shift);
   return cudaSuccess;
 }
 
@@ -654,9 +655,12 @@ static int run(blance_ctx* ctx, blance_plan* pl) {
       for (int i = 0; i < n; ++i) { const int kk = pl->h_insts[i].S > s ? pl->h_insts[i].state_constraints[s] : 0; if (kk >= 1 && kk <= 4) kmask |= 1u << kk; }
       // speculative kernel: 9 scout warps + the leader (warps 4 and 8 stay away from the leader's scheduler) when the
       // GPU has SMs to spare, 3 scouts per CTA for wide batches
+      // warp 0 leads, warp 1 publishes, warp 2 commits, 8 scouts (warps 4 and 8 stay away from the leader's scheduler) / 4 scouts
       const bool spec_wide = 2 * n <= ctx->sm_count;
-      const int spec_nw = spec_wide ? 12 : 4, spec_sw = spec_wide ? 9 : 3;
+      const int spec_nw = spec_wide ? 13 : 7, spec_sw = spec_wide ? 8 : 4;
       const unsigned spec_idle = spec_wide ? ((1u << 4) | (1u << 8)) : 0u;
+      int spec_shift = 0;
+      while ((1 << spec_shift) < spec_sw * SP_D) ++spec_shift;
       const int spec_max_n = std::min(2048, 32 * spec_sw * SP_NPTS);
       bool any_auto = false;
       for (int i = 0; i < n; ++i) any_auto |= pl->h_insts[i].engine == BLANCE_ENGINE_AUTO;
@@ -695,10 +699,10 @@ static int run(blance_ctx* ctx, blance_plan* pl) {
         const size_t sdyn = spec_dyn_smem_bytes(std::min(pl->max_N, spec_max_n), spec_sw);
         size_t* cfgd = g_spec_dyn[ctx->device & 63];
         cudaError_t pe = cudaSuccess;
-        if (pe == cudaSuccess && (kmask & 2u)) pe = launch_pass_spec_k<1>(cfgd + 0, P, n, spec_nw, spec_sw, spec_idle, s, sdyn, st);
-        if (pe == cudaSuccess && (kmask & 4u)) pe = launch_pass_spec_k<2>(cfgd + 1, P, n, spec_nw, spec_sw, spec_idle, s, sdyn, st);
-        if (pe == cudaSuccess && (kmask & 8u)) pe = launch_pass_spec_k<3>(cfgd + 2, P, n, spec_nw, spec_sw, spec_idle, s, sdyn, st);
-        if (pe == cudaSuccess && (kmask & 16u)) pe = launch_pass_spec_k<4>(cfgd + 3, P, n, spec_nw, spec_sw, spec_idle, s, sdyn, st);
+        if (pe == cudaSuccess && (kmask & 2u)) pe = launch_pass_spec_k<1>(cfgd + 0, P, n, spec_nw, spec_sw, spec_idle, spec_shift, s, sdyn, st);
+        if (pe == cudaSuccess && (kmask & 4u)) pe = launch_pass_spec_k<2>(cfgd + 1, P, n, spec_nw, spec_sw, spec_idle, spec_shift, s, sdyn, st);
+        if (pe == cudaSuccess && (kmask & 8u)) pe = launch_pass_spec_k<3>(cfgd + 2, P, n, spec_nw, spec_sw, spec_idle, spec_shift, s, sdyn, st);
+        if (pe == cudaSuccess && (kmask & 16u)) pe = launch_pass_spec_k<4>(cfgd + 3, P, n, spec_nw, spec_sw, spec_idle, spec_shift, s, sdyn, st);
         CK(pe);
         ctx->launches += __builtin_popcount(kmask);
       }
@@ -768,8 +772,9 @@ static int fetch(blance_ctx* ctx, blance_plan* pl, blance_plan_out* outs) {
       std::fprintf(stderr, "[blance] inst %d: steps %lld accepted %lld | resolved by the leader %lld (stale results %lld) movers %lld team %lld rebuilds %lld waits %lld\n",
                    i, fin[i].steps, fin[i].fast_steps, fin[i].spec_resolved, fin[i].spec_stale, fin[i].spec_movers, fin[i].spec_team,
                    fin[i].spec_rebuilds, fin[i].spec_waits),
-      std::fprintf(stderr, "[blance]   leader cycles: scans %lld | waits %lld | resolves %lld | mover updates %lld | team %lld | passes total %lld\n",
-                   fin[i].spec_cyc[0], fin[i].spec_cyc[1], fin[i].spec_cyc[2], fin[i].spec_cyc[3], fin[i].spec_cyc[4], fin[i].spec_cyc[5]);
+      std::fprintf(stderr, "[blance]   leader cycles: scans %lld | waits %lld | resolve loads+keys %lld | picks %lld | mover mirror %lld | list+publish %lld | team %lld | passes total %lld ; team causes: unclean %lld dead %lld exhausted %lld bound %lld\n",
+                   fin[i].spec_cyc[0], fin[i].spec_cyc[1], fin[i].spec_cyc[2], fin[i].spec_cyc[3], fin[i].spec_cyc[4], fin[i].spec_cyc[5], fin[i].spec_cyc[6], fin[i].spec_cyc[7],
+                   fin[i].spec_why[0], fin[i].spec_why[1], fin[i].spec_why[2], fin[i].spec_why[3]);
   for (int i = 0; i < n; ++i) {
     const DInst& D = pl->h_insts[i];
     blance_plan_out& o = outs[i];
@@ -898,8 +903,10 @@ extern "C" int blance_calc_partition_moves(blance_ctx* ctx, int32_t n_parts, int
     if (st != BLANCE_OK) ctx->err = c0->err;
     return st;
   }
-  if (n_parts < 0 || n_states < 0 || n_visit_states < 0 || n_visit_states > n_states || !state_slot_off || max_ops < 0)
-    return fail(ctx, BLANCE_ERR_INVALID_ARG, "blance_calc_partition_moves: bad sizes");
+  if (n_parts < 0 || n_states < 0 || n_states >= 255 || n_visit_states < 0 || n_visit_states > n_states || !state_slot_off || max_ops < 0)
+    return fail(ctx, BLANCE_ERR_INVALID_ARG, "blance_calc_partition_moves: bad sizes (at most 254 states: 0xFF is the \"\" state of a del op)");
+  if (max_ops < 2 * state_slot_off[n_states])
+    return fail(ctx, BLANCE_ERR_INVALID_ARG, "blance_calc_partition_moves: max_ops must be at least 2 * n_slots (no op may be dropped)");
   if (n_parts == 0) return BLANCE_OK;
   const int SL = state_slot_off[n_states];
   if (SL > 0 && (!beg_rows || !end_rows)) return fail(ctx, BLANCE_ERR_INVALID_ARG, "rows are NULL");
@@ -913,7 +920,8 @@ extern "C" int blance_calc_partition_moves(blance_ctx* ctx, int32_t n_parts, int
                o_node = o_end + align_up(rows_b, 256), o_state = o_node + align_up(sizeof(int32_t) * ops, 256),
                o_kind = o_state + align_up(ops, 256), o_cnt = o_kind + align_up(ops, 256),
                total = o_cnt + align_up(sizeof(int32_t) * (size_t)n_parts, 256);
-  CK(cudaMalloc((void**)&d, total));
+  if (cudaMallocAsync((void**)&d, total, st) != cudaSuccess)       // stream-ordered pool: no device-wide sync per call
+    return fail(ctx, BLANCE_ERR_NOMEM, "blance_calc_partition_moves: device allocation failed");
   int rc = BLANCE_OK;
   auto step = [&](cudaError_t e, const char* what) {
     if (e != cudaSuccess && rc == BLANCE_OK) rc = fail(ctx, BLANCE_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
@@ -937,7 +945,155 @@ extern "C" int blance_calc_partition_moves(blance_ctx* ctx, int32_t n_parts, int
     step(cudaMemcpyAsync(op_kind, d + o_kind, (size_t)n_parts * max_ops, cudaMemcpyDeviceToHost, st), "D2H");
   }
   step(cudaMemcpyAsync(op_count, d + o_cnt, sizeof(int32_t) * (size_t)n_parts, cudaMemcpyDeviceToHost, st), "D2H");
+  cudaFreeAsync(d, st);
   step(cudaStreamSynchronize(st), "sync");
-  cudaFree(d);
   return rc;
+}
+
+// ---------------------------------------------------------------------------------------
+// Move lists for the orchestrator (orchestrate.go:273-287, 749-763, 177-186), resident on the device.
+
+struct blance_moves {
+  int32_t n_parts = 0, n_node_ids = 0;
+  long long total_ops = 0;
+  char* arena = nullptr;             // one stream-ordered allocation
+  long long* d_off = nullptr;        // [n_parts + 1]
+  int32_t* d_node = nullptr; uint8_t* d_state = nullptr; uint8_t* d_kind = nullptr;   // CSR ops
+  int32_t* d_next = nullptr;         // [n_parts] cursors of the current round
+  uint32_t *d_key = nullptr, *d_key2 = nullptr; int32_t *d_val = nullptr, *d_val2 = nullptr;   // [n_parts]
+  int32_t* d_ncnt = nullptr; int32_t* d_noff = nullptr; unsigned long long* d_nbest = nullptr; int32_t* d_best = nullptr;   // per node
+  void* d_tmp = nullptr; size_t tmp_bytes = 0;
+};
+
+extern "C" int blance_moves_create(blance_ctx* ctx, int32_t n_parts, int32_t n_states, int32_t n_visit_states,
+                                   const int32_t* state_slot_off, const int32_t* beg_rows, const int32_t* end_rows,
+                                   int32_t favor_min_nodes, int32_t n_node_ids, blance_moves** out, int64_t* total_ops) {
+  if (!ctx) return fail(nullptr, BLANCE_ERR_INVALID_ARG, "ctx is NULL");
+  if (!ctx->children.empty()) ctx = ctx->children[0];
+  if (!out) return fail(ctx, BLANCE_ERR_INVALID_ARG, "blance_moves_create: out is NULL");
+  *out = nullptr;
+  if (n_parts < 0 || n_states < 0 || n_states >= 255 || n_visit_states < 0 || n_visit_states > n_states || !state_slot_off || n_node_ids < 0)
+    return fail(ctx, BLANCE_ERR_INVALID_ARG, "blance_moves_create: bad sizes");
+  const int SL = state_slot_off[n_states];
+  if (n_parts > 0 && SL > 0 && (!beg_rows || !end_rows)) return fail(ctx, BLANCE_ERR_INVALID_ARG, "rows are NULL");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int max_ops = std::max(1, 2 * SL);
+  const size_t P = (size_t)std::max(n_parts, 1), NN = (size_t)std::max(n_node_ids, 1);
+  size_t scan_tmp = 0, sort_tmp = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (const int32_t*)nullptr, (long long*)nullptr, n_parts + 1, st);
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const int32_t*)nullptr, (int32_t*)nullptr, n_parts, 0, 32, st);
+  // scratch of the construction (rows, padded ops, counts) lives in the same arena and is simply left unused later
+  struct Sl { void** p; size_t bytes; };
+  blance_moves* mv = new blance_moves();
+  mv->n_parts = n_parts; mv->n_node_ids = n_node_ids;
+  int32_t *d_slot = nullptr, *d_beg = nullptr, *d_end = nullptr, *p_node = nullptr, *d_cnt = nullptr;
+  uint8_t *p_state = nullptr, *p_kind = nullptr;
+  mv->tmp_bytes = std::max(scan_tmp, sort_tmp) + 256;
+  std::vector<Sl> sl = {
+      {(void**)&mv->d_off, sizeof(long long) * (P + 2)}, {(void**)&mv->d_node, sizeof(int32_t) * P * max_ops},
+      {(void**)&mv->d_state, P * max_ops}, {(void**)&mv->d_kind, P * max_ops}, {(void**)&mv->d_next, sizeof(int32_t) * P},
+      {(void**)&mv->d_key, sizeof(uint32_t) * P}, {(void**)&mv->d_key2, sizeof(uint32_t) * P}, {(void**)&mv->d_val, sizeof(int32_t) * P},
+      {(void**)&mv->d_val2, sizeof(int32_t) * P}, {(void**)&mv->d_ncnt, sizeof(int32_t) * (NN + 1)}, {(void**)&mv->d_noff, sizeof(int32_t) * (NN + 2)},
+      {(void**)&mv->d_nbest, sizeof(unsigned long long) * NN}, {(void**)&mv->d_best, sizeof(int32_t) * NN}, {(void**)&mv->d_tmp, mv->tmp_bytes},
+      {(void**)&d_slot, sizeof(int32_t) * (n_states + 1)}, {(void**)&d_beg, sizeof(int32_t) * P * std::max(SL, 1)},
+      {(void**)&d_end, sizeof(int32_t) * P * std::max(SL, 1)}, {(void**)&p_node, sizeof(int32_t) * P * max_ops},
+      {(void**)&p_state, P * max_ops}, {(void**)&p_kind, P * max_ops}, {(void**)&d_cnt, sizeof(int32_t) * (P + 1)}};
+  size_t total = 0;
+  for (auto& x : sl) total += align_up(x.bytes, 256);
+  if (cudaMallocAsync((void**)&mv->arena, total, st) != cudaSuccess) { delete mv; return fail(ctx, BLANCE_ERR_NOMEM, "blance_moves_create: device allocation failed"); }
+  { size_t off = 0; for (auto& x : sl) { *x.p = mv->arena + off; off += align_up(x.bytes, 256); } }
+  int rc = BLANCE_OK;
+  auto step = [&](cudaError_t e, const char* what) {
+    if (e != cudaSuccess && rc == BLANCE_OK) rc = fail(ctx, BLANCE_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  };
+  step(cudaMemcpyAsync(d_slot, state_slot_off, sizeof(int32_t) * (n_states + 1), cudaMemcpyHostToDevice, st), "H2D");
+  if (n_parts > 0 && SL > 0) {
+    step(cudaMemcpyAsync(d_beg, beg_rows, sizeof(int32_t) * (size_t)n_parts * SL, cudaMemcpyHostToDevice, st), "H2D");
+    step(cudaMemcpyAsync(d_end, end_rows, sizeof(int32_t) * (size_t)n_parts * SL, cudaMemcpyHostToDevice, st), "H2D");
+  }
+  step(cudaMemsetAsync(d_cnt, 0, sizeof(int32_t) * (P + 1), st), "memset");
+  if (rc == BLANCE_OK && n_parts > 0) {
+    k_calc_moves<<<grid_for(ctx, n_parts, 128), 128, 0, st>>>(n_parts, n_states, n_visit_states, d_slot, d_beg, d_end, favor_min_nodes,
+                                                             max_ops, p_node, p_state, p_kind, d_cnt);
+    size_t tb = mv->tmp_bytes;
+    step(cub::DeviceScan::ExclusiveSum(mv->d_tmp, tb, d_cnt, mv->d_off, n_parts + 1, st), "scan");
+    k_moves_compact<<<grid_for(ctx, n_parts, 128), 128, 0, st>>>(n_parts, max_ops, mv->d_off, d_cnt, p_node, p_state, p_kind,
+                                                                mv->d_node, mv->d_state, mv->d_kind);
+    step(cudaGetLastError(), "k_calc_moves / k_moves_compact");
+    ctx->launches += 2;
+    step(cudaMemcpyAsync(&mv->total_ops, mv->d_off + n_parts, sizeof(long long), cudaMemcpyDeviceToHost, st), "D2H");
+  } else {
+    step(cudaMemsetAsync(mv->d_off, 0, sizeof(long long) * (P + 2), st), "memset");
+  }
+  step(cudaStreamSynchronize(st), "sync");
+  if (rc != BLANCE_OK) { cudaFreeAsync(mv->arena, st); delete mv; return rc; }
+  if (total_ops) *total_ops = mv->total_ops;
+  *out = mv;
+  return BLANCE_OK;
+}
+
+extern "C" int blance_moves_fetch(blance_ctx* ctx, blance_moves* mv, int64_t* op_off, int32_t* op_node, uint8_t* op_state, uint8_t* op_kind) {
+  if (!ctx || !mv) return fail(ctx, BLANCE_ERR_INVALID_ARG, "ctx or moves is NULL");
+  if (!ctx->children.empty()) ctx = ctx->children[0];
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  if (op_off) CK(cudaMemcpyAsync(op_off, mv->d_off, sizeof(long long) * ((size_t)mv->n_parts + 1), cudaMemcpyDeviceToHost, st));
+  if (mv->total_ops > 0) {
+    if (op_node) CK(cudaMemcpyAsync(op_node, mv->d_node, sizeof(int32_t) * (size_t)mv->total_ops, cudaMemcpyDeviceToHost, st));
+    if (op_state) CK(cudaMemcpyAsync(op_state, mv->d_state, (size_t)mv->total_ops, cudaMemcpyDeviceToHost, st));
+    if (op_kind) CK(cudaMemcpyAsync(op_kind, mv->d_kind, (size_t)mv->total_ops, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  return BLANCE_OK;
+}
+
+extern "C" int blance_moves_available(blance_ctx* ctx, blance_moves* mv, const int32_t* next, int32_t* node_off, int32_t* node_parts,
+                                      int32_t* best_part) {
+  if (!ctx || !mv || !next) return fail(ctx, BLANCE_ERR_INVALID_ARG, "ctx, moves or next is NULL");
+  if (!ctx->children.empty()) ctx = ctx->children[0];
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int P = mv->n_parts, NN = mv->n_node_ids;
+  CK(cudaMemsetAsync(mv->d_ncnt, 0, sizeof(int32_t) * ((size_t)NN + 1), st));
+  CK(cudaMemsetAsync(mv->d_nbest, 0xFF, sizeof(unsigned long long) * (size_t)std::max(NN, 1), st));
+  if (P > 0) {
+    CK(cudaMemcpyAsync(mv->d_next, next, sizeof(int32_t) * (size_t)P, cudaMemcpyHostToDevice, st));
+    k_moves_next<<<grid_for(ctx, P, 256), 256, 0, st>>>(P, NN, mv->d_off, mv->d_node, mv->d_kind, mv->d_next, mv->d_key, mv->d_val,
+                                                       mv->d_ncnt, mv->d_nbest);
+    size_t tb = mv->tmp_bytes;
+    CK(cub::DeviceRadixSort::SortPairs(mv->d_tmp, tb, mv->d_key, mv->d_key2, mv->d_val, mv->d_val2, P, 0, 32, st));   // stable: partitions stay ascending
+    ctx->launches += 1;
+  }
+  {
+    size_t tb = mv->tmp_bytes;
+    CK(cub::DeviceScan::ExclusiveSum(mv->d_tmp, tb, mv->d_ncnt, mv->d_noff, NN + 1, st));
+  }
+  if (NN > 0) { k_moves_best<<<(NN + 255) / 256, 256, 0, st>>>(NN, mv->d_nbest, mv->d_best); ctx->launches += 1; }
+  CK(cudaGetLastError());
+  int32_t n_avail = 0;
+  CK(cudaMemcpyAsync(&n_avail, mv->d_noff + NN, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (node_off) CK(cudaMemcpyAsync(node_off, mv->d_noff, sizeof(int32_t) * ((size_t)NN + 1), cudaMemcpyDeviceToHost, st));
+  if (best_part && NN > 0) CK(cudaMemcpyAsync(best_part, mv->d_best, sizeof(int32_t) * (size_t)NN, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (node_parts && n_avail > 0) {
+    CK(cudaMemcpyAsync(node_parts, mv->d_val2, sizeof(int32_t) * (size_t)n_avail, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  return BLANCE_OK;
+}
+
+extern "C" void blance_moves_free(blance_ctx* ctx, blance_moves* mv) {
+  if (!mv) return;
+  if (ctx && !ctx->children.empty()) ctx = ctx->children[0];
+  if (ctx) {
+    std::lock_guard<std::mutex> g(ctx->mu);
+    cudaSetDevice(ctx->device);
+    if (mv->arena) cudaFreeAsync(mv->arena, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+  } else if (mv->arena) cudaFree(mv->arena);
+  delete mv;
 }

@@ -57,7 +57,8 @@ struct DInst {
   long long fast_steps;    // steps decided without a full evaluation (sequencer windows / accepted scout results)
   // counters of the speculative kernel (whole plan)
   long long spec_resolved, spec_movers, spec_team, spec_rebuilds, spec_waits, spec_stale;
-  long long spec_cyc[6];   // leader cycles: group scans, waits, resolves, mover updates, team calls, whole passes
+  long long spec_cyc[8];   // leader cycles: scans | waits | resolve loads+keys | resolve picks | mover mirror | mover list+publish | team | passes
+  long long spec_why[4];   // team evaluations by cause: row not clean | current node dead | candidates ran out | bound test failed
 };
 
 struct DPool {
@@ -78,6 +79,7 @@ struct DPool {
   // speculative pass: n2n's deviation from the all-sticky hypothesis, the per-step hypothesis counts
   // (qstat[step][4]) and the (top, node) pair sort that produces them
   int32_t* n2n_dev; int32_t* qstat;
+  uint8_t* srank;          // [sum PU] per step: 0x80 | ranks of its current nodes when the step was accepted as sticky
   unsigned long long* pair_keys; unsigned long long* pair_keys_alt;
   uint32_t* pair_vals; uint32_t* pair_vals_alt;
   DInst* insts;

@@ -652,6 +652,159 @@ PartitionMap UninternPlan(const InternedPlan& ip, const PlanOutBuffers& ob, Warn
   return next;
 }
 
+// ---- the JSON wire form (api.go:30,35) --------------------------------------------------------------------
+// encoding/json, default options: strings are quoted with ", \\ and control characters escaped (\n \r \t short
+// forms, others \u00XX), <, > and & as \u003c \u003e \u0026 (HTML-safe), U+2028 / U+2029 as \u2028 / \u2029,
+// invalid UTF-8 as U+FFFD; map keys are sorted by their bytes; a nil slice is null.
+static void json_string(std::string& out, const std::string& v) {
+  static const char* hex = "0123456789abcdef";
+  out.push_back('"');
+  const unsigned char* p = reinterpret_cast<const unsigned char*>(v.data());
+  const size_t n = v.size();
+  for (size_t i = 0; i < n;) {
+    const unsigned char c = p[i];
+    if (c < 0x80) {
+      if (c == '"' || c == '\\') { out.push_back('\\'); out.push_back(char(c)); }
+      else if (c == '\n') out += "\\n";
+      else if (c == '\r') out += "\\r";
+      else if (c == '\t') out += "\\t";
+      else if (c < 0x20 || c == '<' || c == '>' || c == '&') { out += "\\u00"; out.push_back(hex[c >> 4]); out.push_back(hex[c & 15]); }
+      else out.push_back(char(c));
+      ++i;
+      continue;
+    }
+    // decode one UTF-8 sequence the way Go's utf8.DecodeRuneInString does (shortest form, no surrogates, <= U+10FFFF)
+    size_t len = 0;
+    uint32_t cp = 0;
+    if (c >= 0xC2 && c <= 0xDF) { len = 2; cp = c & 0x1F; }
+    else if (c >= 0xE0 && c <= 0xEF) { len = 3; cp = c & 0x0F; }
+    else if (c >= 0xF0 && c <= 0xF4) { len = 4; cp = c & 0x07; }
+    bool ok = len != 0 && i + len <= n;
+    for (size_t k = 1; ok && k < len; ++k) {
+      const unsigned char d = p[i + k];
+      unsigned char lo = 0x80, hi = 0xBF;
+      if (k == 1) {
+        if (c == 0xE0) lo = 0xA0;
+        if (c == 0xED) hi = 0x9F;
+        if (c == 0xF0) lo = 0x90;
+        if (c == 0xF4) hi = 0x8F;
+      }
+      if (d < lo || d > hi) ok = false;
+      cp = (cp << 6) | (d & 0x3F);
+    }
+    if (!ok) { out += "\\ufffd"; ++i; continue; }
+    if (cp == 0x2028 || cp == 0x2029) { out += "\\u202"; out.push_back(hex[cp & 15]); }
+    else out.append(v, i, len);
+    i += len;
+  }
+  out.push_back('"');
+}
+
+template <class GetList>   // GetList(state index) -> (present, is_nil, list writer)
+static void json_partition(std::string& out, const std::string& name, const std::vector<std::pair<const std::string*, const OptStrs*>>& states) {
+  out += "{\"name\":";
+  json_string(out, name);
+  out += ",\"nodesByState\":{";
+  bool first = true;
+  for (const auto& st : states) {
+    if (!first) out.push_back(',');
+    first = false;
+    json_string(out, *st.first);
+    out.push_back(':');
+    if (!*st.second) { out += "null"; continue; }
+    out.push_back('[');
+    bool f2 = true;
+    for (const auto& n : **st.second) {
+      if (!f2) out.push_back(',');
+      f2 = false;
+      json_string(out, n);
+    }
+    out.push_back(']');
+  }
+  out += "}}";
+}
+
+std::string PartitionMapToJSON(const PartitionMap& m) {
+  std::vector<const std::pair<const std::string, Partition>*> entries;
+  entries.reserve(m.size());
+  for (const auto& kv : m) entries.push_back(&kv);
+  std::sort(entries.begin(), entries.end(), [](auto* a, auto* b) { return a->first < b->first; });   // byte order = Go's key order
+  std::vector<std::string> chunks(entries.size());
+  parallel_for(entries.size(), [&](size_t lo, size_t hi, int) {
+    std::vector<std::pair<const std::string*, const OptStrs*>> states;
+    for (size_t i = lo; i < hi; ++i) {
+      const Partition& part = entries[i]->second;
+      states.clear();
+      for (const auto& kv : part.NodesByState) states.push_back({&kv.first, &kv.second});
+      std::sort(states.begin(), states.end(), [](const auto& a, const auto& b) { return *a.first < *b.first; });
+      std::string& out = chunks[i];
+      json_string(out, entries[i]->first);
+      out.push_back(':');
+      json_partition<int>(out, part.Name, states);
+    }
+  });
+  size_t total = 2;
+  for (const auto& c : chunks) total += c.size() + 1;
+  std::string out;
+  out.reserve(total);
+  out.push_back('{');
+  for (size_t i = 0; i < chunks.size(); ++i) {
+    if (i) out.push_back(',');
+    out += chunks[i];
+  }
+  out.push_back('}');
+  return out;
+}
+
+// rows -> JSON directly (the next map of a plan; same bytes as PartitionMapToJSON(UninternPlan(...)))
+std::string PlanResultToJSON(const InternedPlan& ip, const PlanOutBuffers& ob) {
+  const blance_plan_in& in = ip.in;
+  std::vector<int32_t> ids;
+  for (int32_t p = 0; p < in.n_parts; ++p)
+    if (ip.part_in_assign[size_t(p)]) ids.push_back(p);
+  std::sort(ids.begin(), ids.end(), [&](int32_t a, int32_t b) { return ip.part_names[size_t(a)] < ip.part_names[size_t(b)]; });
+  std::vector<int32_t> state_order(size_t(in.n_states));
+  for (int32_t s = 0; s < in.n_states; ++s) state_order[size_t(s)] = s;
+  std::sort(state_order.begin(), state_order.end(), [&](int32_t a, int32_t b) { return ip.state_names[size_t(a)] < ip.state_names[size_t(b)]; });
+  std::vector<std::string> chunks(ids.size());
+  parallel_for(ids.size(), [&](size_t lo, size_t hi, int) {
+    std::vector<OptStrs> lists(size_t(in.n_states));
+    std::vector<std::pair<const std::string*, const OptStrs*>> states;
+    for (size_t i = lo; i < hi; ++i) {
+      const int32_t p = ids[i];
+      const int32_t* row = ob.next_rows.data() + size_t(p) * size_t(in.n_slots);
+      states.clear();
+      for (int32_t s : state_order) {
+        const uint8_t sh = ob.next_shape[size_t(p) * size_t(in.n_states) + size_t(s)];
+        if (sh == BLANCE_SHAPE_ABSENT) continue;
+        OptStrs& l = lists[size_t(s)];
+        if (sh == BLANCE_SHAPE_NIL) l = std::nullopt;
+        else {
+          l = Strs{};
+          for (int32_t j = ip.state_slot_off[size_t(s)]; j < ip.state_slot_off[size_t(s) + 1] && row[j] != BLANCE_NO_NODE; ++j)
+            l->push_back(ip.node_names[size_t(row[j])]);
+        }
+        states.push_back({&ip.state_names[size_t(s)], &l});
+      }
+      std::string& out = chunks[i];
+      json_string(out, ip.part_names[size_t(p)]);
+      out.push_back(':');
+      json_partition<int>(out, ip.part_names[size_t(p)], states);
+    }
+  });
+  std::string out;
+  size_t total = 2;
+  for (const auto& c : chunks) total += c.size() + 1;
+  out.reserve(total);
+  out.push_back('{');
+  for (size_t i = 0; i < chunks.size(); ++i) {
+    if (i) out.push_back(',');
+    out += chunks[i];
+  }
+  out.push_back('}');
+  return out;
+}
+
 // plan.go:49-52: after any non-matching iteration the caller's maps hold the new partitions; when the loop
 // ends their content equals the returned map.  Map surgery (new keys) is serial, the deep copies are not.
 void ReplayCallerMutation(const PartitionMap& next, PartitionMap& prevMap, PartitionMap& partitionsToAssign) {

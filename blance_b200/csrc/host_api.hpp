@@ -40,6 +40,16 @@ struct Partition {                     // api.go:28-36
 };
 using PartitionMap = std::unordered_map<std::string, Partition>;   // api.go:24 (values, not pointers)
 
+// The JSON wire form of a PartitionMap, byte for byte what Go's encoding/json produces for
+// map[string]*Partition with the tags of api.go:30,35 (`json:"name"`, `json:"nodesByState"`): object keys sorted
+// by their bytes, a nil slice as null, strings escaped with encoding/json's default (HTML-safe) rules.
+// The per-partition objects are rendered in parallel for large maps.
+std::string PartitionMapToJSON(const PartitionMap& m);
+// The same for the flat result of a plan (rows -> JSON without building the PartitionMap first).
+struct InternedPlan;
+struct PlanOutBuffers;
+std::string PlanResultToJSON(const InternedPlan& ip, const PlanOutBuffers& ob);
+
 struct PartitionModelState { int Priority = 0; int Constraints = 0; };   // api.go:46-62
 using PartitionModel = std::unordered_map<std::string, PartitionModelState>;
 

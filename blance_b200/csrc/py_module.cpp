@@ -82,7 +82,8 @@ struct PyOut { std::unique_ptr<PlanOutBuffers> ob; const InternedPlan* ip; };
 
 PYBIND11_MODULE(_host, m) {
   m.doc() = "blance_b200 host API (C++ mirror of blance's api.go over the CUDA C ABI)";
-  py::register_exception<BlanceError>(m, "BlanceError");
+  // a subclass of the pure-Python blance_b200.abi.BlanceError, so one except clause covers the ctypes face too
+  py::register_exception<BlanceError>(m, "BlanceError", py::module_::import("blance_b200.abi").attr("BlanceError"));
 
   m.def(
       "PlanNextMapEx",
@@ -128,6 +129,9 @@ PYBIND11_MODULE(_host, m) {
     for (const auto& op : CalcPartitionMoves(states, beg, end, favor)) out.emplace_back(op.Node, op.State, op.Op);
     return out;
   });
+
+  m.def("PartitionMapToJSON", [](const PyPartitionMap& m) { return py::bytes(PartitionMapToJSON(to_map(m))); },
+        "the JSON wire form of a PartitionMap (api.go:30,35), byte for byte what Go's encoding/json emits");
 
   m.def("CalcPartitionMovesMap", [](const Strs& states, const PyPartitionMap& beg, const PyPartitionMap& end, bool favor) {
     std::unordered_map<std::string, std::vector<std::tuple<std::string, std::string, std::string>>> out;
@@ -223,6 +227,9 @@ PYBIND11_MODULE(_host, m) {
     PartitionMap next = UninternPlan(*ip.ip, *out.ob, &w);
     return py::make_tuple(from_map(next), w);
   });
+
+  m.def("plan_result_to_json", [](const PyInterned& ip, const PyOut& out) { return py::bytes(PlanResultToJSON(*ip.ip, *out.ob)); },
+        "rows of a plan result -> the JSON wire form of the next map, without building the PartitionMap");
 
   // the product C ABI on already-interned tables (GPU): returns the status code
   m.def("run_plan_cuda", [](const PyInterned& ip, PyOut& out) {

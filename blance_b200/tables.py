@@ -6,7 +6,7 @@ import ctypes
 
 import numpy as np
 
-from . import api
+from . import abi as api      # ctypes structs + lazy library handle: importing tables loads no native code
 
 NO_NODE = -1
 SHAPE_ABSENT, SHAPE_NIL, SHAPE_LIST = 0, 1, 2
@@ -198,6 +198,42 @@ class Context:
             op_state.ctypes.data, op_kind.ctypes.data, op_count.ctypes.data)
         self._check(st, "blance_calc_partition_moves")
         return op_node, op_state, op_kind, op_count
+
+    def moves_create(self, slot_off, beg_rows, end_rows, favor_min_nodes, n_node_ids, n_visit_states=None):
+        """blance_moves_create: CalcPartitionMoves of every partition, resident on the device in CSR form.
+        Returns (handle, total_ops)."""
+        slot_off = np.ascontiguousarray(slot_off, np.int32)
+        beg = np.ascontiguousarray(beg_rows, np.int32)
+        end = np.ascontiguousarray(end_rows, np.int32)
+        n_states = len(slot_off) - 1
+        h, tot = ctypes.c_void_p(), ctypes.c_int64()
+        st = self.lib.blance_moves_create(self.ptr, beg.shape[0], n_states, n_states if n_visit_states is None else n_visit_states,
+                                          slot_off.ctypes.data, beg.ctypes.data, end.ctypes.data, int(bool(favor_min_nodes)),
+                                          int(n_node_ids), ctypes.byref(h), ctypes.byref(tot))
+        self._check(st, "blance_moves_create")
+        return (h, beg.shape[0], int(n_node_ids)), int(tot.value)
+
+    def moves_fetch(self, handle, total_ops):
+        h, n_parts, _ = handle
+        off = np.zeros(n_parts + 1, np.int64)
+        node = np.zeros(max(1, total_ops), np.int32)
+        state = np.zeros(max(1, total_ops), np.uint8)
+        kind = np.zeros(max(1, total_ops), np.uint8)
+        self._check(self.lib.blance_moves_fetch(self.ptr, h, off.ctypes.data, node.ctypes.data, state.ctypes.data, kind.ctypes.data), "blance_moves_fetch")
+        return off, node[:total_ops], state[:total_ops], kind[:total_ops]
+
+    def moves_available(self, handle, next_idx):
+        h, n_parts, n_node_ids = handle
+        nxt = np.ascontiguousarray(next_idx, np.int32)
+        node_off = np.zeros(n_node_ids + 1, np.int32)
+        node_parts = np.zeros(max(1, n_parts), np.int32)
+        best = np.zeros(max(1, n_node_ids), np.int32)
+        self._check(self.lib.blance_moves_available(self.ptr, h, nxt.ctypes.data, node_off.ctypes.data, node_parts.ctypes.data, best.ctypes.data),
+                    "blance_moves_available")
+        return node_off, node_parts[:node_off[-1]], best[:n_node_ids]
+
+    def moves_free(self, handle):
+        self.lib.blance_moves_free(self.ptr, handle[0])
 
     def kernel_launches(self):
         return int(self.lib.blance_ctx_kernel_launches(self.ptr))

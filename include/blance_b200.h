@@ -198,6 +198,34 @@ int blance_calc_partition_moves(blance_ctx* ctx, int32_t n_parts, int32_t n_stat
                                 const int32_t* end_rows, int32_t favor_min_nodes, int32_t max_ops,
                                 int32_t* op_node, uint8_t* op_state, uint8_t* op_kind, int32_t* op_count);
 
+/* ---- move lists for the orchestrator (orchestrate.go:273-287, 749-763, 177-186) ----------------------------
+ * OrchestrateMoves seeds one NextMoves{Moves: CalcPartitionMoves(...)} per partition (orchestrate.go:273-287),
+ * then repeatedly rebuilds "which partitions have their NEXT move on node n" by scanning every partition
+ * (findAvailableMovesUnlocked, orchestrate.go:749-763) and lets the FindMoveFunc pick one per node
+ * (LowestWeightPartitionMoveForNode, orchestrate.go:177-186: the lowest MoveOpWeight wins).  A blance_moves
+ * handle keeps all move lists on the device in CSR form; blance_moves_available() answers one round of the
+ * scan for a vector of cursors.
+ *   Order: the reference appends in Go map order (random); here every per-node list is in ascending partition
+ *   index, and ties of the lowest weight go to the lowest partition index. */
+typedef struct blance_moves blance_moves;
+
+/* beg_rows / end_rows / state_slot_off / n_visit_states / favor_min_nodes as in blance_calc_partition_moves.
+ * n_node_ids bounds the node ids that occur in the rows.  *total_ops receives the number of ops of all
+ * partitions together (the size of the op_* arrays blance_moves_fetch fills). */
+int blance_moves_create(blance_ctx* ctx, int32_t n_parts, int32_t n_states, int32_t n_visit_states,
+                        const int32_t* state_slot_off, const int32_t* beg_rows, const int32_t* end_rows,
+                        int32_t favor_min_nodes, int32_t n_node_ids, blance_moves** out, int64_t* total_ops);
+/* CSR copy-out: op_off[n_parts+1]; op_node / op_state / op_kind [total_ops], partition p owns [op_off[p], op_off[p+1]). */
+int blance_moves_fetch(blance_ctx* ctx, blance_moves* moves, int64_t* op_off, int32_t* op_node, uint8_t* op_state,
+                       uint8_t* op_kind);
+/* One round of findAvailableMovesUnlocked for cursors next[n_parts] (NextMoves.Next): node_off[n_node_ids+1] and
+ * node_parts[<= n_parts] list, per node, the partitions whose next move is on it (ascending partition index);
+ * best_part[n_node_ids] is the FindMoveFunc's pick with MoveOpWeight {promote 1, demote 2, add 3, del 4}, or -1
+ * when the node has no available move.  Any output pointer may be NULL. */
+int blance_moves_available(blance_ctx* ctx, blance_moves* moves, const int32_t* next, int32_t* node_off,
+                           int32_t* node_parts, int32_t* best_part);
+void blance_moves_free(blance_ctx* ctx, blance_moves* moves);
+
 #ifdef __cplusplus
 }
 #endif

@@ -465,3 +465,40 @@ FO_EXPORT int oracle_fast_calc_partition_moves(int32_t n_parts, int32_t n_states
   }
   return BLANCE_OK;
 }
+
+/* One round of findAvailableMovesUnlocked (orchestrate.go:749-763) over CSR move lists, followed by
+ * LowestWeightPartitionMoveForNode (orchestrate.go:177-186, MoveOpWeight orchestrate.go:189-194) per node.
+ * The reference walks a Go map (random order); this restatement - like the product - walks partitions in
+ * ascending index, so per-node lists are ascending and weight ties go to the lowest partition index. */
+FO_EXPORT int oracle_fast_moves_available(int32_t n_parts, int32_t n_node_ids, const int64_t* op_off,
+                                          const int32_t* op_node, const uint8_t* op_kind, const int32_t* next,
+                                          int32_t* node_off, int32_t* node_parts, int32_t* best_part) {
+  static const int weight[4] = {3 /* add */, 4 /* del */, 1 /* promote */, 2 /* demote */};
+  for (int32_t n = 0; n <= n_node_ids; n++) node_off[n] = 0;
+  for (int32_t p = 0; p < n_parts; p++) {
+    int64_t len = op_off[p + 1] - op_off[p];
+    if (next[p] < 0 || next[p] >= len) continue;                      /* nextMoves.Next < len(nextMoves.Moves) */
+    int32_t node = op_node[op_off[p] + next[p]];
+    if (node >= 0 && node < n_node_ids) node_off[node + 1]++;
+  }
+  for (int32_t n = 0; n < n_node_ids; n++) node_off[n + 1] += node_off[n];
+  int32_t* fill = (int32_t*)malloc(sizeof(int32_t) * ((size_t)n_node_ids + 1));
+  memcpy(fill, node_off, sizeof(int32_t) * ((size_t)n_node_ids + 1));
+  for (int32_t p = 0; p < n_parts; p++) {
+    int64_t len = op_off[p + 1] - op_off[p];
+    if (next[p] < 0 || next[p] >= len) continue;
+    int32_t node = op_node[op_off[p] + next[p]];
+    if (node >= 0 && node < n_node_ids) node_parts[fill[node]++] = p;
+  }
+  free(fill);
+  for (int32_t n = 0; n < n_node_ids; n++) {
+    int32_t r = -1, rw = 0;
+    for (int32_t i = node_off[n]; i < node_off[n + 1]; i++) {          /* r = 0; if weight[moves[r]] > weight[move] r = i */
+      int32_t p = node_parts[i];
+      int w = weight[op_kind[op_off[p] + next[p]] & 3];
+      if (r < 0 || rw > w) { r = p; rw = w; }
+    }
+    best_part[n] = r;
+  }
+  return BLANCE_OK;
+}

@@ -9,6 +9,7 @@
 #include "literal.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <unordered_set>
@@ -411,8 +412,17 @@ InnerResult plan_next_map_inner(const PartitionMap& prev_map, const PartitionMap
     std::unordered_map<std::string, IntMap> node_to_node_counts;    // plan.go:266
 
     int64_t done = 0;
+    auto slice_t0 = std::chrono::steady_clock::now();
+    int64_t in_slice = 0;
     for (auto& partition : order) {                                  // plan.go:268-302
       if (opts.max_steps_per_pass >= 0 && done++ >= opts.max_steps_per_pass) break;
+      if (opts.slice_seconds && opts.slice_steps > 0 && in_slice == opts.slice_steps) {
+        const auto now = std::chrono::steady_clock::now();
+        opts.slice_seconds->push_back(std::chrono::duration<double>(now - slice_t0).count());
+        slice_t0 = now;
+        in_slice = 0;
+      }
+      ++in_slice;
       int64_t partition_weight = 1;
       if (opts.partition_weights) {
         auto w = opts.partition_weights->find(partition->name);
@@ -434,6 +444,8 @@ InnerResult plan_next_map_inner(const PartitionMap& prev_map, const PartitionMap
       partition->nodes_by_state[state_name] = nodes_to_assign;       // plan.go:299
       adjust_state_node_counts(state_node_counts, state_name, deref(nodes_to_assign), partition_weight);
     }
+    if (opts.slice_seconds && opts.slice_steps > 0 && in_slice == opts.slice_steps)
+      opts.slice_seconds->push_back(std::chrono::duration<double>(std::chrono::steady_clock::now() - slice_t0).count());
   };
 
   for (const auto& state_name : sort_state_names(model)) {          // plan.go:307-324

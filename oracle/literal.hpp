@@ -66,6 +66,11 @@ struct Options {                         // api.go:183-190 (+ the package-level 
   // Optional cap on how many partitions each state pass processes (bench.py's
   // bounded cpu_baseline sample; <0 = no cap).  Not part of the reference.
   int64_t max_steps_per_pass = -1;
+  // Optional timing of the greedy chain in slices of `slice_steps` consecutive findBestNodes steps (bench.py's
+  // reference arm: every slice is one bounded sample of the workload; the copies and sorts around the passes are
+  // outside the slices).  slice_seconds receives one entry per completed slice.  Not part of the reference.
+  int64_t slice_steps = 0;
+  std::vector<double>* slice_seconds = nullptr;
 };
 
 using Warnings = std::unordered_map<std::string, Strs>;

@@ -68,10 +68,13 @@ PYBIND11_MODULE(_literal, m) {
          const std::optional<IntMap>& msc, const std::optional<IntMap>& pw, const std::optional<IntMap>& ss,
          const std::optional<IntMap>& nw, const std::optional<StrMap>& nh,
          const std::optional<std::unordered_map<std::string, std::vector<std::pair<int64_t, int64_t>>>>& hr,
-         int booster, int max_iterations, int64_t max_steps_per_pass) {
+         int booster, int max_iterations, int64_t max_steps_per_pass, int64_t slice_steps) {
         PartitionModel pm;
         for (const auto& kv : model) pm[kv.first] = {kv.second.first, kv.second.second};
         Options o = make_options(msc, pw, ss, nw, nh, hr, booster, max_iterations, max_steps_per_pass);
+        std::vector<double> slices;
+        o.slice_steps = slice_steps;
+        if (slice_steps > 0) o.slice_seconds = &slices;
         PartitionMap prev_map = to_map(prev);
         PartitionMap assign_map;
         // None = the caller passed the SAME map object twice (plan_test.go:1716-1718)
@@ -93,6 +96,7 @@ PYBIND11_MODULE(_literal, m) {
         out["iterations"] = r.iterations;
         out["steps"] = r.steps;
         out["seconds"] = secs;
+        out["slice_seconds"] = slices;
         return out;
       },
       py::arg("prev_map"), py::arg("partitions_to_assign"), py::arg("nodes_all"), py::arg("nodes_to_remove"),
@@ -100,7 +104,7 @@ PYBIND11_MODULE(_literal, m) {
       py::arg("partition_weights") = py::none(), py::arg("state_stickiness") = py::none(),
       py::arg("node_weights") = py::none(), py::arg("node_hierarchy") = py::none(),
       py::arg("hierarchy_rules") = py::none(), py::arg("booster") = 0, py::arg("max_iterations") = 10,
-      py::arg("max_steps_per_pass") = -1);
+      py::arg("max_steps_per_pass") = -1, py::arg("slice_steps") = 0);
 
   m.def("calc_partition_moves",
         [](const Strs& states, const NodesByState& beg, const NodesByState& end, bool favor_min_nodes) {

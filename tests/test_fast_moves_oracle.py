@@ -73,3 +73,40 @@ def test_fast_moves_equal_literal_on_random_partitions(chunk):
         want = [tuple(m) for m in L.calc_partition_moves(names[:n_visit], beg, end, favor)]
         got = run_fast(names, n_visit, caps, nodes, beg, end, favor)
         assert got == want, (names[:n_visit], beg, end, favor)
+
+
+def test_moves_available_oracle_matches_the_go_statements():
+    """oracle_fast_moves_available against a direct Python reading of findAvailableMovesUnlocked
+    (orchestrate.go:749-763) + LowestWeightPartitionMoveForNode (orchestrate.go:177-194) with partitions walked
+    in ascending index (the one order the reference leaves to Go's map iteration)."""
+    import ctypes
+    import numpy as np
+    FAST.oracle_fast_moves_available.argtypes = [ctypes.c_int32] * 2 + [ctypes.c_void_p] * 7
+    weight = {"promote": 1, "demote": 2, "add": 3, "del": 4}
+    kinds = ["add", "del", "promote", "demote"]          # enum blance_op_kind
+    rng = np.random.default_rng(3)
+    for trial in range(200):
+        P, NN = int(rng.integers(0, 30)), int(rng.integers(1, 8))
+        lens = rng.integers(0, 5, P)
+        off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        tot = int(off[-1])
+        node = rng.integers(0, NN, max(tot, 1)).astype(np.int32)
+        kind = rng.integers(0, 4, max(tot, 1)).astype(np.uint8)
+        nxt = rng.integers(0, 6, max(P, 1)).astype(np.int32)
+        available = {}
+        for p in range(P):                                # for _, nextMoves := range o.mapPartitionToNextMoves
+            if nxt[p] < lens[p]:                          # if nextMoves.Next < len(nextMoves.Moves)
+                available.setdefault(int(node[off[p] + nxt[p]]), []).append(p)
+        best = {}
+        for n, moves in available.items():
+            r = 0
+            for i, p in enumerate(moves):                 # if MoveOpWeight[moves[r].Op] > MoveOpWeight[move.Op] { r = i }
+                if weight[kinds[kind[off[moves[r]] + nxt[moves[r]]]]] > weight[kinds[kind[off[p] + nxt[p]]]]:
+                    r = i
+            best[n] = moves[r]
+        r_off = np.zeros(NN + 1, np.int32); r_parts = np.zeros(max(P, 1), np.int32); r_best = np.zeros(NN, np.int32)
+        assert FAST.oracle_fast_moves_available(P, NN, off.ctypes.data, node.ctypes.data, kind.ctypes.data, nxt.ctypes.data,
+                                                r_off.ctypes.data, r_parts.ctypes.data, r_best.ctypes.data) == 0
+        for n in range(NN):
+            assert list(r_parts[r_off[n]:r_off[n + 1]]) == available.get(n, []), (trial, n)
+            assert r_best[n] == best.get(n, -1), (trial, n)

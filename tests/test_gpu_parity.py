@@ -340,6 +340,47 @@ def test_calc_partition_moves_vectorised(ctx):
             assert np.array_equal(got[0][m], on[m]) and np.array_equal(got[1][m], os_[m]) and np.array_equal(got[2][m], ok[m])
 
 
+def test_moves_plan_csr_and_available_moves(ctx):
+    """blance_moves_*: the orchestrator's seeding (orchestrate.go:273-287) as device-resident CSR move lists, one
+    round of findAvailableMovesUnlocked (orchestrate.go:749-763) for random cursors and the lowest-MoveOpWeight pick
+    per node (orchestrate.go:177-186), against the oracle restatement."""
+    FAST.oracle_fast_moves_available.argtypes = [ctypes.c_int32] * 2 + [ctypes.c_void_p] * 7
+    rng = np.random.default_rng(11)
+    for favor, caps, NN in ((0, (1, 2), 40), (1, (1, 2, 1), 12), (0, (2, 2, 2), 9)):
+        S = len(caps)
+        slot_off = np.concatenate([[0], np.cumsum(caps)]).astype(np.int32)
+        P, SL = 20000, int(slot_off[-1])
+
+        def rows():
+            r = np.full((P, SL), -1, np.int32)
+            for p in range(P):
+                perm = rng.permutation(NN)[:SL]
+                for s_ in range(S):
+                    n = rng.integers(0, caps[s_] + 1)
+                    r[p, slot_off[s_]:slot_off[s_] + n] = perm[slot_off[s_]:slot_off[s_] + n]
+            return r
+        beg, end = rows(), rows()
+        max_ops = 2 * SL
+        on = np.zeros((P, max_ops), np.int32); os_ = np.zeros((P, max_ops), np.uint8)
+        ok = np.zeros((P, max_ops), np.uint8); oc = np.zeros(P, np.int32)
+        assert FAST.oracle_fast_calc_partition_moves(P, S, S, slot_off.ctypes.data, beg.ctypes.data, end.ctypes.data, favor, max_ops,
+                                                     on.ctypes.data, os_.ctypes.data, ok.ctypes.data, oc.ctypes.data) == 0
+        h, total = ctx.moves_create(slot_off, beg, end, favor, NN)
+        off, node, state, kind = ctx.moves_fetch(h, total)
+        ref_off = np.concatenate([[0], np.cumsum(oc)]).astype(np.int64)
+        assert total == int(oc.sum()) and np.array_equal(off, ref_off)
+        m = np.arange(max_ops)[None, :] < oc[:, None]
+        assert np.array_equal(node, on[m]) and np.array_equal(state, os_[m]) and np.array_equal(kind, ok[m])
+        for rnd in range(3):
+            nxt = rng.integers(0, max_ops + 1, P).astype(np.int32) if rnd else np.zeros(P, np.int32)
+            node_off, node_parts, best = ctx.moves_available(h, nxt)
+            r_off = np.zeros(NN + 1, np.int32); r_parts = np.zeros(P, np.int32); r_best = np.zeros(NN, np.int32)
+            assert FAST.oracle_fast_moves_available(P, NN, ref_off.ctypes.data, node.ctypes.data, kind.ctypes.data, nxt.ctypes.data,
+                                                    r_off.ctypes.data, r_parts.ctypes.data, r_best.ctypes.data) == 0
+            assert np.array_equal(node_off, r_off) and np.array_equal(node_parts, r_parts[:r_off[-1]]) and np.array_equal(best, r_best)
+        ctx.moves_free(h)
+
+
 def test_invalid_arguments_are_status_codes(ctx):
     t = synth.make_fresh(1)
     t.top_state = 7
