@@ -11,7 +11,7 @@ complete PlanNextMapEx (all convergence iterations, plan.go:23-58).
               time from CUDA events on the library's stream, max over ranks
   e2e         the same through blance_plan_next_map with HOST buffers: staging, H2D,
               all kernels, D2H inside the timed region
-  roofline    of the dominant kernel k_assign_pass: algorithmic bytes per findBestNodes
+  roofline    of the dominant kernel k_assign_pass_spec: algorithmic bytes per findBestNodes
               step (16*N + (N/8)(1+R*k) + 8*slots + 12) x steps /
               its device time, against the measured HBM copy bandwidth
   cpu_baseline  the literal C++ restatement of the Go planner (oracle/literal.cpp: string
@@ -19,12 +19,18 @@ complete PlanNextMapEx (all convergence iterations, plan.go:23-58).
               sample of the same cluster shape, 1 core (the reference planner is
               single-goroutine).  Go itself cannot run here (no toolchain).
 
---gpus N: the greedy chain of one plan is sequential (each step reads the counts the
-previous step wrote), so one plan does not shard; N ranks plan N independent clusters
-of the named shape (distinct seeds) — "replicas only", weak scaling, no collective in
-the data path; torch.distributed(nccl) is used for the barrier and the max over ranks.
+  parity      sha256 of the result next to the oracle's (profiles/parity_cfg4.json); e2e_string_api: the same
+              plan through the string API (maps of strings in and out); batch_cfg5: BASELINE config 5
+              (1 024 instances in one blance_plan_next_map_batch call) on this GPU
 
---impl reference: the CPU arm — the literal oracle on the box's host cores (rank 0 only).
+--gpus N: the greedy chain of one plan is sequential (each step reads the counts the
+previous step wrote), so one plan does not shard; N ranks plan the SAME cluster, one plan
+per GPU — "replicas only", weak scaling, no collective in the data path;
+torch.distributed(nccl) is used for the barrier and the max over ranks.  What shards is the
+batch: tools/bench_cfg5.py runs config 5 over 1/2/4/8 GPUs through blance_ctx_create_multi.
+
+--impl reference: the CPU arm — slices of the real workload's first inner plan through the
+literal oracle on the box's host cores (rank 0 only).
 """
 import argparse
 import json
@@ -116,7 +122,7 @@ def literal_slices(parts, n_slices, slice_steps):
     kw["partitions_to_assign"] = None                  # the same map object twice, as blance's callers do
     kw["max_iterations"] = 1
     per_pass = ((n_slices + 1) // 2) * slice_steps
-    r = L.plan_next_map_ex(**kw, max_steps_per_pass=per_pass, slice_steps=slice_steps)
+    r = L.plan_next_map_ex(**kw, max_steps_per_pass=per_pass, slice_steps=slice_steps, memoize_partition_scores=True)
     return list(r["slice_seconds"])[:n_slices]
 
 
@@ -205,6 +211,8 @@ def main():
     ap.add_argument("--cpu-sample-parts", type=int, default=1024)
     ap.add_argument("--cpu-slice-steps", type=int, default=256, help="findBestNodes steps per reference-arm bench step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-string-api", action="store_true")
+    ap.add_argument("--no-batch", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -231,7 +239,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    t = synth.make_rebalance(CFG, P=args.parts, seed_offset=rank)
+    # every rank plans the SAME cluster (replicas): the chain's length depends on the data, so different seeds per rank
+    # would make the max over ranks a property of the slowest seed rather than of the machine
+    t = synth.make_rebalance(CFG, P=args.parts)
     ctx = tables.Context(local_rank)
     plan = ctx.upload(t)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > L2 (126 MB)
@@ -263,6 +273,11 @@ def main():
     if dist is not None:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     total_ms_max, pass_ms_max = float(tt[0]), float(tt[1])
+    per_rank = [total_ms / args.steps]
+    if dist is not None:
+        g = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(g, torch.tensor([total_ms / args.steps], dtype=torch.float64, device=dev))
+        per_rank = [float(x[0]) for x in g]
 
     # ---- end to end through the C ABI with host buffers -----------------------------------
     h2d = sum(np.asarray(getattr(t, f)).nbytes for f in
@@ -293,6 +308,63 @@ def main():
     moves_s = time.perf_counter() - t0
     moves_ops = int(mv[3].sum())
 
+    # ---- outside every timed region: the result's digest next to the oracle's (profiles/parity_cfg4.json, written by
+    # tools/make_parity_digest.py; the full arrays are compared in tests/test_gpu_parity.py::test_cfg4_full_size_bit_exact)
+    import hashlib
+    parity = {"sha256_gpu": hashlib.sha256(np.ascontiguousarray(res.next_rows).tobytes()).hexdigest(), "sha256_oracle": None,
+              "iters_run": iters, "steps": steps_per_plan}
+    try:
+        with open(os.path.join(ROOT, "profiles", "parity_cfg4.json")) as f:
+            pj = json.load(f)
+        if args.parts is None and pj.get("n_parts") == t.n_parts:
+            parity["sha256_oracle"] = pj["sha256_next_rows"]
+            parity["equal"] = (parity["sha256_gpu"] == pj["sha256_next_rows"] and iters == pj["iters_run"] and steps_per_plan == pj["steps"])
+    except Exception:
+        pass
+
+    # ---- the string API end to end (PartitionMap of strings in and out: InternPlan + C ABI + UninternPlan + the caller-map
+    # mutation of plan.go:49-52), on the same cluster, rank 0 only; the map is built natively (no Python dicts in the timing)
+    string_api = None
+    if rank == 0 and not args.no_string_api:
+        import blance_b200
+        removed = np.nonzero(t.node_removed)[0].tolist()
+        added = np.nonzero(t.node_added)[0].tolist()
+        reps = []
+        for _ in range(2):       # the first call pays the page faults of its fresh allocations
+            d = blance_b200._host.bench_string_api(t.prev_rows, t.n_nodes, [int(x) for x in t.state_constraints], removed, added,
+                                                   t.node_weight, t.part_weight, t.part_has_weight, [int(x) for x in t.state_stickiness], 10)
+            reps.append(d)
+        d = reps[-1]
+        string_api = {"value": t.n_parts / (d["total_ms"] / 1e3), "unit": UNIT, "ms": d["total_ms"], "first_call_ms": reps[0]["total_ms"],
+                      "intern_ms": d["intern_ms"], "c_abi_call_ms": d["call_ms"], "unintern_ms": d["unintern_ms"],
+                      "caller_map_mutation_ms": d["mutate_ms"], "host_threads": d["host_threads"],
+                      "result_equals_resident_run": bool(np.array_equal(d["next_rows"], res.next_rows)),
+                      "note": "blance.PlanNextMapEx of the C++ host twin (host_api.cpp) on %d string partitions; what a Go host "
+                              "pays when it does not keep its maps interned" % t.n_parts}
+
+    # ---- BASELINE config 5 on this GPU: 1 024 independent instances (multi-tenant fan-out) in one batch call; the struct
+    # arrays are built once, the timed call is blance_plan_next_map_batch alone (H2D, all kernels, D2H inside)
+    batch = None
+    if rank == 0 and not args.no_batch:
+        n_inst = 1024
+        fresh = [synth.make_fresh(5, seed_offset=i) for i in range(n_inst)]
+        prep = ctx.prepare_batch(fresh)
+        got = ctx.run_batch(prep)
+        rebs = [synth.make_rebalance(5, g.next_rows, seed_offset=i) for i, g in enumerate(got)]
+        prep2 = ctx.prepare_batch(rebs)
+        ctx.run_batch(prep2)                                  # warm-up
+        ts_ = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            r5 = ctx.run_batch(prep2)
+            ts_.append(time.perf_counter() - t0)
+        best = min(ts_)
+        parts5 = sum(x.n_parts for x in rebs)
+        batch = {"workload": "cfg5: %d independent PlanNextMapEx instances (1024 partitions x 64 nodes, rack rules), rebalance stage" % n_inst,
+                 "value": parts5 / best, "unit": UNIT, "ms": 1e3 * best, "instances_per_s": n_inst / best,
+                 "device_ms": float(r5[0].device_ms), "n_gpus": 1,
+                 "note": "wall time of the C call with host buffers; multi-GPU sharding of the batch: tools/bench_cfg5.py, profiles/"}
+
     if rank == 0:
         P, N = t.n_parts, t.n_nodes
         value = world * P * args.steps / (total_ms_max / 1e3)
@@ -301,35 +373,30 @@ def main():
         peak, peak_src = measured_peak()
         pass_s = pass_ms_max / 1e3
         achieved = steps_per_plan * args.steps * bytes_per_step / pass_s / 1e9 if pass_s > 0 else None
-        os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
-        if args.parts is None:
-            try:
-                with open(os.path.join(ROOT, "profiles", "workload_cfg4.json"), "w") as f:
-                    json.dump({"workload": "cfg4", "n_parts": P, "n_nodes": N, "iterations": iters,
-                               "findBestNodes_steps": steps_per_plan, "steps_per_partition": steps_per_plan / P}, f)
-            except OSError:
-                pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 score / int32 tables", "data": "synthetic",
-            "config": {"workload": "cfg4: PlanNextMapEx %d partitions x %d nodes, k=(1,2), node+partition weights, stickiness, "
-                                   "-16/+16 nodes; one step = one complete plan (%d convergence iterations, %d findBestNodes steps)"
-                                   % (P, N, iters, steps_per_plan),
-                       "steps_per_partition": steps_per_plan / P,
-                       "findBestNodes_steps_per_s": world * steps_per_plan * args.steps / (total_ms_max / 1e3),
-                       "sticky_fraction": sticky / max(1, steps_per_plan),
-                       "parallelism": "replicas only: %d independent plan(s), one per GPU; no data-path collective" % world,
-                       "l2": "256 MiB device buffer rewritten between timed iterations (L2 flush)",
-                       "timing": "CUDA events on the library stream, max over ranks"},
+            "config": shared_config(P, N),
+            "run": {"step": "one complete plan (%d convergence iterations, %d findBestNodes steps)" % (iters, steps_per_plan),
+                    "steps_per_partition_measured": steps_per_plan / P,
+                    "findBestNodes_steps_per_s": world * steps_per_plan * args.steps / (total_ms_max / 1e3),
+                    "accepted_fraction": sticky / max(1, steps_per_plan),
+                    "parallelism": "replicas only: %d rank(s) plan the same cluster, one plan per GPU; no data-path collective" % world,
+                    "ms_per_step_per_rank": per_rank,
+                    "l2": "256 MiB device buffer rewritten between timed iterations (L2 flush)",
+                    "timing": "CUDA events on the library stream, max over ranks"},
+            "parity": parity,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * e2e_total / args.steps, "result_equals_resident_run": same},
             "calc_partition_moves": {"partitions_per_s": P / moves_s, "ms": 1e3 * moves_s, "ops": moves_ops,
                                      "note": "moves.go:41-119 for all partitions in one launch, prevMap -> nextMap, host buffers "
                                              "(H2D of both maps and D2H of the op lists inside the timed call)"},
+            "e2e_string_api": string_api,
+            "batch_cfg5": batch,
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_assign_pass_seq + k_assign_pass (the two assign-pass kernels; per pass one of them runs)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_assign_pass_spec (the speculative assign pass; k_assign_pass runs the passes that do not qualify)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(steps_per_plan * args.steps / max(1, pass_launches)),
                          "peak_source": peak_src, "bytes_per_findBestNodes_step": bytes_per_step,
                          "steps_per_launch": steps_per_plan * args.steps / max(1, pass_launches),
@@ -349,6 +416,9 @@ def main():
                           "per partition of the full workload" % (args.cpu_sample_parts, N, st, sec, spp),
                 "best_cpu_array_oracle": {"value": fst / fsec / spp, "unit": UNIT, "findBestNodes_steps_per_s": fst / fsec,
                                           "sample": "oracle/fast.c, 32768 x %d, one inner plan" % N}}
+            line["cpu_array_oracle"] = dict(line["cpu_baseline"]["best_cpu_array_oracle"], cores=1, kind="port",
+                                            note="the best CPU restatement we have (array form, O(N) arg-min per pick): the ratio "
+                                                 "to THIS says what the GPU kernel buys; the literal restatement above is the reference's cost")
         print(json.dumps(line), flush=True)
     ctx.free(plan)
     ctx.close()

@@ -46,17 +46,13 @@ namespace blance_dev {
 #define SP_LPL 2             // list entries per leader lane
 #define SP_D 2               // ring chunks per scout warp
 #define SP_NPTS 8            // nodes per scout thread in team operations (N <= 32 * SW * SP_NPTS)
-#define SP_LMIN 10           // rebuild the list when fewer entries are left (and it is not complete)
 
 enum : int { SPB_ALL = 8, SPB_GO = 9, SPB_DONE = 10, SPB_TEAM = 11 };
-enum : int32_t { SP_OP_EXIT = 1, SP_OP_REBUILD = 2, SP_OP_FULL = 3 };
+enum : int32_t { SP_OP_EXIT = 1, SP_OP_FULL = 3 };
 enum : uint32_t { SPZ_NEVER = 0x80000000u };
 
 struct SpecCtl {
   uint4 xchg[2][32];                 // team arg-min partials
-  uint4 cand[64];                    // rebuild: extracted {key hi, key lo, node, -}
-  uint4 bound[32];                   // rebuild: per-warp lower bound of what was not extracted
-  uint4 ins[16];                     // list inserts of a mover
   uint4 pubq[64];                    // leader -> publisher: {A offset or -1, delta, epoch, 1 = last entry of its epoch}
   alignas(16) int32_t slot_bit[BL_SLP_MAX];
   alignas(8) unsigned long long mbar[32 * SP_D];
@@ -69,7 +65,7 @@ struct SpecCtl {
 __host__ __device__ inline size_t spec_dyn_smem_bytes(int N, int SW) {
   const size_t H = (size_t)32 * SW * SP_D;
   const size_t Np = ((size_t)N + 3) & ~(size_t)3;        // every array starts 16-byte aligned
-  size_t b = Np * 32 + Np * 4 + Np * 4 + ((Np + 15) & ~(size_t)15);
+  size_t b = Np * 32 + Np * 8 + Np * 4 + Np * 4 + ((Np + 15) & ~(size_t)15);   // mirror, base keys, totals, stamps, flags
   b += H * 64 + H * 16 + H * 16 + H;   // records (<= 16 words), qstat, results, accepted ranks
   return b;
 }
@@ -135,6 +131,15 @@ __device__ __forceinline__ Best warp_argmin_q(Best v) {
   return Best{mhi, mlo, __reduce_min_sync(full, p2)};
 }
 
+// base key: the score with nodeToNodeCounts = 0 and no stickiness (cd + 0/P == cd exactly)
+__device__ __forceinline__ unsigned long long sp_base_key(double cd, double ff, double wd, double wy, bool boost, bool has_nw) {
+  const double base = __dadd_rn(cd, ff);
+  double r = base;
+  if (has_nw && !boost) r = div_exact(r, wd, wy);
+  if (boost) { double b = -wd; if (b < 0.0) b = 0.0; r = __dadd_rn(base, b); }
+  return score_key(r);
+}
+
 __device__ __forceinline__ bool lex_lt(unsigned long long ka, uint32_t pa, unsigned long long kb, uint32_t pb) {
   return ka < kb || (ka == kb && pa < pb);
 }
@@ -144,7 +149,7 @@ __device__ __forceinline__ bool lex_lt(unsigned long long ka, uint32_t pa, unsig
 // (it applies the movers' updates of A and publishes the epochs, so that the leader never waits for a fence
 // over global atomics), the rest are the SW scouts.  SW * SP_D must be a power of two (swd_shift = its log2).
 template <int K>
-__global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, int SW, unsigned idle_mask, int swd_shift) {
+__global__ void __launch_bounds__(448, 1) k_assign_pass_spec(DPool pool, int s, int SW, unsigned idle_mask, int swd_shift) {
   DInst& D = pool.insts[blockIdx.x];
   if (!D.active || s >= D.S || D.pass_mode != 2) return;
   if (D.state_constraints[s] != K) return;
@@ -188,7 +193,8 @@ __global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, 
   const uint32_t base_a = (uint32_t)__cvta_generic_to_shared(dyn_smem);
   const uint32_t Np = ((uint32_t)N + 3u) & ~3u;                  // (padded: every array starts 16-byte aligned)
   const uint32_t nd_a = base_a;                                  // mirror: {cd, ff, wd, wy} per node
-  const uint32_t tot_a = nd_a + 32u * Np;                        // all-state totals
+  const uint32_t bk_a = nd_a + 32u * Np;                         // base key of every node (score with n2n = 0, no stickiness)
+  const uint32_t tot_a = bk_a + 8u * Np;                         // all-state totals
   const uint32_t chg_a = tot_a + 4u * Np;                        // lastchg
   const uint32_t flg_a = chg_a + 4u * Np;                        // NF_VALID | NF_BOOST
   const uint32_t rec_a = flg_a + ((Np + 15u) & ~15u);            // ring: records
@@ -228,6 +234,7 @@ __global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, 
     const double ff = have_p ? div_exact(__dmul_rn(0.001, (double)t), Pd, Py) : 0.0;   // plan.go:650
     double* nd = reinterpret_cast<double*>(dyn_smem) + 4 * (size_t)n;
     nd[0] = cd; nd[1] = ff; nd[2] = wd; nd[3] = wy;
+    *reinterpret_cast<unsigned long long*>(dyn_smem + (bk_a - base_a) + 8u * n) = sp_base_key(cd, ff, wd, wy, (fl & NF_BOOST) != 0, has_nw);
     sts32(tot_a + 4u * n, t);
     sts32(chg_a + 4u * n, 0);
     dyn_smem[(flg_a - base_a) + n] = (unsigned char)fl;
@@ -243,14 +250,14 @@ __global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, 
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   bar_sync(SPB_ALL, NTA);
 
-  uint32_t slot_blocked = 0;                 // bit sl: a listed node found in slot sl of the row is not a candidate
+  uint32_t slot_blocked = 0;                 // bit sl: slot sl belongs to a higher-priority state (its node is not a candidate)
   uint32_t slot_state_s = 0;                 //         slot sl belongs to the state being assigned
   uint32_t sbit8[8];                         // state bit of slot sl
 #pragma unroll
   for (int sl = 0; sl < 8; ++sl) sbit8[sl] = sl < SL ? (uint32_t)lds32(sbit_a + 4u * sl) : 0u;
   for (int sl = 0; sl < SL && sl < 8; ++sl) {
     const uint32_t b = (uint32_t)lds32(sbit_a + 4u * sl);
-    if (b & (higher_states | (1u << s))) slot_blocked |= 1u << sl;
+    if (b & higher_states) slot_blocked |= 1u << sl;
     if (b & (1u << s)) slot_state_s |= 1u << sl;
   }
 
@@ -267,7 +274,6 @@ __global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, 
     xbuf ^= 1;
     return warp_argmin(Best{(uint32_t)e.x, (uint32_t)e.y, (uint32_t)e.z});
   };
-  const int M_ext = (64 / SW) < 7 ? (64 / SW) : 7;       // rebuild: entries extracted per scout warp
 
   if (is_pub) {
     // =================================== publisher =====================================================
@@ -373,7 +379,7 @@ __global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, 
           bar_sync(SPB_GO, NTT);
           const int op = *(volatile int32_t*)&ctl.cmd_op;
           if (op == SP_OP_EXIT) goto scouts_done;
-          bool changed = true;
+          bool changed = false;
           const int32_t E1 = *(volatile int32_t*)&ctl.cmd_epoch;
           if (op == SP_OP_FULL) {
             // ---- full evaluation of step cmd_arg (the lock-step kernel's step) from the mirror --------------
@@ -461,41 +467,9 @@ __global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, 
                     if (have_p) nd[1] = div_exact(__dmul_rn(0.001, (double)t), Pd, Py);
                   }
                   sts32(chg_a + 4u * n, E1);
+                  *reinterpret_cast<unsigned long long*>(dyn_smem + (bk_a - base_a) + 8u * n) =
+                      sp_base_key(cd, nd[1], nd[2], nd[3], (dyn_smem[(flg_a - base_a) + n] & NF_BOOST) != 0, has_nw);
                 }
-              }
-            }
-            if (changed) bar_sync(SPB_TEAM, TS);          // the mirror is final before the base keys are read
-          }
-          if (changed) {
-            // ---- rebuild: every scout warp extracts its M_ext smallest base keys and a lower bound of the rest ---
-            unsigned long long bkey[SP_NPTS];
-            uint32_t live = 0;
-#pragma unroll
-            for (int j = 0; j < SP_NPTS; ++j) {
-              const int n = team_node(j);
-              bkey[j] = ~0ull;
-              if (n < N && (dyn_smem[(flg_a - base_a) + n] & NF_VALID)) {
-                const int4 ma = lds128(nd_a + (uint32_t)n * 32u), mb = lds128(nd_a + (uint32_t)n * 32u + 16u);
-                const uint32_t fl = dyn_smem[(flg_a - base_a) + n];
-                bkey[j] = sp_key(__hiloint2double(ma.y, ma.x), __hiloint2double(ma.w, ma.z), __hiloint2double(mb.y, mb.x),
-                                 __hiloint2double(mb.w, mb.z), (fl & NF_BOOST) != 0, has_nw, 0, 0.0, have_p, Pd, Py);
-                live |= 1u << j;
-              }
-            }
-            for (int r = 0; r <= M_ext; ++r) {
-              unsigned long long bk = ~0ull;
-              uint32_t bpos = 0xFFFFFFFFu;
-#pragma unroll
-              for (int j = 0; j < SP_NPTS; ++j)
-                if (((live >> j) & 1u) && (bpos == 0xFFFFFFFFu || bkey[j] < bk)) { bk = bkey[j]; bpos = (uint32_t)team_node(j); }
-              const Best b = warp_argmin(Best{(uint32_t)(bk >> 32), (uint32_t)bk, bpos});
-              if (r < M_ext) {
-                if (lane == 0) ctl.cand[sidx * M_ext + r] = make_uint4(b.hi, b.lo, b.pos, 0u);
-#pragma unroll
-                for (int j = 0; j < SP_NPTS; ++j)
-                  if ((uint32_t)team_node(j) == b.pos) live &= ~(1u << j);
-              } else if (lane == 0) {
-                ctl.bound[sidx] = make_uint4(b.hi, b.lo, b.pos, 0u);      // all-ones when nothing is left
               }
             }
           }
@@ -602,15 +576,21 @@ __global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, 
   int32_t Ln[SP_LPL];
 #pragma unroll
   for (int u = 0; u < SP_LPL; ++u) { Lk[u] = ~0ull; Ln[u] = -1; }
-  unsigned long long ubk = ~0ull, B0k = ~0ull;
-  uint32_t ubp = 0xFFFFFFFFu, B0p = 0xFFFFFFFFu;
+  unsigned long long ubk = ~0ull, B0k = ~0ull, lb1k = ~0ull;      // lb1: lower bound of the second-column entries
+  uint32_t ubp = 0xFFFFFFFFu, B0p = 0xFFFFFFFFu, lb1p = 0xFFFFFFFFu;
+  long long n_round2 = 0;
   int32_t E = 0;
-  int seq = 0, pub_head = 0;
-  long long n_fast = 0, n_res = 0, n_mov = 0, n_team = 0, n_reb = 0, n_wait = 0, n_stale = 0;
+  int seq = 0, pub_head = 0, movers_since_rebuild = 0;
+  bool b0_clamped = false;
+  long long n_fast = 0, n_res = 0, n_mov = 0, n_team = 0, n_reb = 0, n_wait = 0, n_stale = 0, n_cwait = 0;
   long long why[4] = {0, 0, 0, 0};
   long long cyc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc = clock64();
   const long long t_begin = tc;
+#ifdef BLANCE_SPEC_TIMING
 #define SP_T(ix) do { const long long n_ = clock64(); cyc[ix] += n_ - tc; tc = n_; } while (0)
+#else
+#define SP_T(ix) do { } while (0)
+#endif
 
   auto team_cmd = [&](int op, int arg) {
     if (lane == 0) {
@@ -624,6 +604,17 @@ __global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, 
     bar_sync(SPB_GO, NTT);
     if (op != SP_OP_EXIT) bar_sync(SPB_DONE, NTT);
   };
+  // The list.  Lane l owns the nodes n = l (mod 32): its two entries are (after a rebuild) the two smallest base
+  // keys of its class and (ublk, ublp) bounds every unlisted node of the class from below; ub = the smallest of
+  // the 32 lane bounds.  Updates stay inside the owner lane; a rebuild is a scan of the base keys in shared
+  // memory by the leader alone.  B0 = min(smallest listed key, ub) is a lower bound of every live base key.
+  unsigned long long ublk = ~0ull;
+  uint32_t ublp = 0xFFFFFFFFu;
+  auto recompute_ub = [&]() {
+    const Best b = warp_argmin_q(Best{(uint32_t)(ublk >> 32), (uint32_t)ublk, ublp});
+    ubk = ((unsigned long long)b.hi << 32) | b.lo;
+    ubp = b.pos;
+  };
   auto recompute_b0 = [&]() {
     unsigned long long bk = ~0ull;
     uint32_t bp = 0xFFFFFFFFu;
@@ -631,28 +622,61 @@ __global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, 
     for (int u = 0; u < SP_LPL; ++u)
       if (Ln[u] >= 0 && lex_lt(Lk[u], (uint32_t)Ln[u], bk, bp)) { bk = Lk[u]; bp = (uint32_t)Ln[u]; }
     const Best b = warp_argmin_q(Best{(uint32_t)(bk >> 32), (uint32_t)bk, bp});
-    if (b.pos != 0xFFFFFFFFu) { B0k = ((unsigned long long)b.hi << 32) | b.lo; B0p = b.pos; }
-    else { B0k = ubk; B0p = ubp; }
+    B0k = ((unsigned long long)b.hi << 32) | b.lo;
+    B0p = b.pos;
+    b0_clamped = !lex_lt(B0k, B0p, ubk, ubp);
+    if (b0_clamped) { B0k = ubk; B0p = ubp; }
   };
-  auto adopt_list = [&]() {                 // after a team rebuild: cand[] / bound[] -> list, ub, B0
-    uint4 bb = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);
-    if (lane < SW) bb = ctl.bound[lane];
-    const Best ub = warp_argmin(Best{bb.x, bb.y, bb.z});
-    ubk = ((unsigned long long)ub.hi << 32) | ub.lo;
-    ubp = ub.pos;
-    const int n_cand = SW * M_ext;
-#pragma unroll
-    for (int u = 0; u < SP_LPL; ++u) {
-      Lk[u] = ~0ull; Ln[u] = -1;
-      const int x = lane + 32 * u;
-      if (x < n_cand) {
-        const uint4 c = ctl.cand[x];
-        const unsigned long long k = ((unsigned long long)c.x << 32) | c.y;
-        if (c.z != 0xFFFFFFFFu && lex_lt(k, c.z, ubk, ubp)) { Lk[u] = k; Ln[u] = (int32_t)c.z; }
+  auto rebuild_list = [&]() {               // the two smallest base keys of my class, and the third as my bound
+    unsigned long long k0 = ~0ull, k1 = ~0ull, k2 = ~0ull;
+    uint32_t n0 = 0xFFFFFFFFu, n1 = 0xFFFFFFFFu, n2 = 0xFFFFFFFFu;
+    for (int n = lane; n < N; n += 32) {
+      if (!(dyn_smem[(flg_a - base_a) + n] & NF_VALID)) continue;
+      const unsigned long long k = *reinterpret_cast<const volatile unsigned long long*>(dyn_smem + (bk_a - base_a) + 8u * n);
+      if (lex_lt(k, (uint32_t)n, k2, n2)) {
+        if (lex_lt(k, (uint32_t)n, k1, n1)) {
+          k2 = k1; n2 = n1;
+          if (lex_lt(k, (uint32_t)n, k0, n0)) { k1 = k0; n1 = n0; k0 = k; n0 = (uint32_t)n; }
+          else { k1 = k; n1 = (uint32_t)n; }
+        } else { k2 = k; n2 = (uint32_t)n; }
       }
     }
+    Lk[0] = k0; Ln[0] = (int32_t)n0; Lk[1] = k1; Ln[1] = (int32_t)n1;      // (n = 0xFFFFFFFF reads as -1: no entry)
+    ublk = k2; ublp = n2;
+    recompute_ub();
+    {
+      const Best b = warp_argmin_q(Best{(uint32_t)(k1 >> 32), (uint32_t)k1, n1});
+      lb1k = ((unsigned long long)b.hi << 32) | b.lo;
+      lb1p = b.pos;
+    }
     recompute_b0();
+    movers_since_rebuild = 0;
     ++n_reb;
+  };
+  // a node whose base key changed: its owner lane updates / lists / bounds it.  tk is its new key (tvalid: live)
+  auto list_touch = [&](int32_t tx, unsigned long long tk, bool tvalid) {
+    bool ub_moved = false;
+    if ((tx & 31) == lane) {
+      if (Ln[0] == tx) { if (tvalid) Lk[0] = tk; else { Ln[0] = -1; Lk[0] = ~0ull; } }
+      else if (Ln[1] == tx) { if (tvalid) Lk[1] = tk; else { Ln[1] = -1; Lk[1] = ~0ull; } }
+      else if (tvalid && lex_lt(tk, (uint32_t)tx, ublk, ublp)) {          // below my bound: it has to be listed
+        if (Ln[0] < 0) { Ln[0] = tx; Lk[0] = tk; }
+        else if (Ln[1] < 0) { Ln[1] = tx; Lk[1] = tk; }
+        else {
+          const int big = lex_lt(Lk[0], (uint32_t)Ln[0], Lk[1], (uint32_t)Ln[1]) ? 1 : 0;
+          unsigned long long ek = tk;
+          uint32_t en = (uint32_t)tx;                                     // the one that stays out: the largest of the three
+          if (lex_lt(tk, (uint32_t)tx, Lk[big], (uint32_t)Ln[big])) { ek = Lk[big]; en = (uint32_t)Ln[big]; Lk[big] = tk; Ln[big] = tx; }
+          if (lex_lt(ek, en, ublk, ublp)) { ublk = ek; ublp = en; ub_moved = true; }
+        }
+      }
+      if (Ln[0] >= 0 && Ln[1] >= 0 && lex_lt(Lk[1], (uint32_t)Ln[1], Lk[0], (uint32_t)Ln[0])) {   // smaller entry first
+        const unsigned long long k = Lk[0]; Lk[0] = Lk[1]; Lk[1] = k;
+        const int32_t n = Ln[0]; Ln[0] = Ln[1]; Ln[1] = n;
+      } else if (Ln[0] < 0 && Ln[1] >= 0) { Lk[0] = Lk[1]; Ln[0] = Ln[1]; Lk[1] = ~0ull; Ln[1] = -1; }
+    }
+    if (tvalid && lex_lt(tk, (uint32_t)tx, lb1k, lb1p)) { lb1k = tk; lb1p = (uint32_t)tx; }   // lb1 only has to be a lower bound
+    if (__any_sync(0xFFFFFFFFu, ub_moved)) recompute_ub();
   };
   // Hands epoch E + 1 to the publisher: the A updates of the lanes with `has`, then the marker that lets it
   // publish.  The mirror / lastchg stores above are ordinary shared-memory stores of this warp, issued before
@@ -669,63 +693,94 @@ __global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, 
     ++E;
   };
 
-  team_cmd(SP_OP_REBUILD, 0);
-  adopt_list();
+  rebuild_list();
   SP_T(6);
 
   int i = 0;
+  // The leader looks at the steps in aligned windows of 64 (two per lane).  A window is loaded once - results,
+  // current nodes, and the stamp test of every result - and stays in registers: after a mover the rest of the
+  // window is judged again from the registers (a result whose current node the mover touched is dropped, the
+  // others only meet the new B0), so a mover costs a ballot, not a reload.
+  int w = -64;                                   // base of the window in registers
+  int4 r[2];
+  int32_t cn[2][K];
+  uint32_t slotv[2];
+  bool have[2], never[2], fresh[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) { r[u] = make_int4(0, 0, 0, 0); slotv[u] = 0; have[u] = never[u] = fresh[u] = false; for (int q = 0; q < K; ++q) cn[u][q] = 0; }
   while (i < n_assign) {
-    // ---- 64 steps (two per lane): accept the leading run of results that are still exact and sticky ------------
-    int4 r[2];
-    int32_t cn[2][K];
-    uint32_t reca[2], slotv[2];
-    bool have[2], never[2], fresh[2], ok[2];
+    if (i >= w + 64) {
+      w = i & ~63;
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int j = i + 32 * u + lane;
-      const uint32_t cj = (uint32_t)j >> 5;
-      const uint32_t slot = ((cj & swd_mask) << 5) | ((uint32_t)j & 31u);
-      slotv[u] = slot;
-      reca[u] = rec_a + slot * RECB;
-      r[u] = lds128(dyn_a + slot * 16u);
+      for (int u = 0; u < 2; ++u) {
+        const int j = w + 32 * u + lane;
+        const uint32_t cj = (uint32_t)j >> 5;
+        const uint32_t slot = ((cj & swd_mask) << 5) | ((uint32_t)j & 31u);
+        slotv[u] = slot;
+        r[u] = lds128(dyn_a + slot * 16u);
 #pragma unroll
-      for (int q = 0; q < K; ++q) cn[u][q] = lds32(reca[u] + (uint32_t)(lo_s + q) * 4u);
-      have[u] = j < n_assign && (((uint32_t)r[u].z >> 21) & 0x3FFu) == ((cj >> swd_shift) & 0x3FFu);
-      never[u] = ((uint32_t)r[u].z & SPZ_NEVER) != 0;
-      fresh[u] = have[u] && !never[u];
-    }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (fresh[u]) {
-#pragma unroll
-        for (int q = 0; q < K; ++q) fresh[u] = fresh[u] && lds32(chg_a + 4u * (uint32_t)cn[u][q]) <= r[u].w;
+        for (int q = 0; q < K; ++q) cn[u][q] = lds32(rec_a + slot * RECB + (uint32_t)(lo_s + q) * 4u);
+        have[u] = j < n_assign && (((uint32_t)r[u].z >> 21) & 0x3FFu) == ((cj >> swd_shift) & 0x3FFu);
+        never[u] = ((uint32_t)r[u].z & SPZ_NEVER) != 0;
+        fresh[u] = have[u] && !never[u];
       }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        if (fresh[u]) {
+#pragma unroll
+          for (int q = 0; q < K; ++q) fresh[u] = fresh[u] && lds32(chg_a + 4u * (uint32_t)cn[u][q]) <= r[u].w;
+        }
+    }
+    // ---- accept the leading run of results that are exact and sticky ------------------------------------------------
+    const int done = i - w;                        // window positions below `done` are behind the leader
+    bool ok[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
       const unsigned long long T = ((unsigned long long)(uint32_t)r[u].x << 32) | (uint32_t)r[u].y;
-      ok[u] = fresh[u] && lex_lt(T, (uint32_t)r[u].z & 0x1FFFu, B0k, B0p);
+      ok[u] = (32 * u + lane < done) || (fresh[u] && lex_lt(T, (uint32_t)r[u].z & 0x1FFFu, B0k, B0p));
     }
     const uint32_t okm0 = __ballot_sync(0xFFFFFFFFu, ok[0]), okm1 = __ballot_sync(0xFFFFFFFFu, ok[1]);
-    const int run = okm0 != 0xFFFFFFFFu ? (__ffs(~okm0) - 1) : (okm1 != 0xFFFFFFFFu ? 32 + (__ffs(~okm1) - 1) : 64);
+    const int f = okm0 != 0xFFFFFFFFu ? (__ffs(~okm0) - 1) : (okm1 != 0xFFFFFFFFu ? 32 + (__ffs(~okm1) - 1) : 64);
 #pragma unroll
     for (int u = 0; u < 2; ++u)
-      if (32 * u + lane < run)                                            // accepted: the committer does the rest
+      if (32 * u + lane >= done && 32 * u + lane < f)                     // accepted: the committer does the rest
         dyn_smem[(acc_a - base_a) + slotv[u]] = (unsigned char)(0x80u | (((uint32_t)r[u].z >> 13) & 0xFFu));
-    i += run;
-    n_fast += run;
+    n_fast += f - done;
+    i = w + f;
     __syncwarp();
-    if (run > 0 && lane == 0) sts32v(front_a, i);
-    if (run == 64 || i >= n_assign) continue;
+    if (f > done && lane == 0) sts32v(front_a, i);
+    if (f == 64 || i >= n_assign) continue;
     SP_T(0);
     // ---- step i was not accepted -----------------------------------------------------------------------------------
+    const uint32_t slot_i = ((((uint32_t)i >> 5) & swd_mask) << 5) | ((uint32_t)i & 31u);
     {
-      const bool hv = run < 32 ? have[0] : have[1];
-      const bool st = run < 32 ? (have[0] && !never[0] && !fresh[0]) : (have[1] && !never[1] && !fresh[1]);
-      const bool have_i = __shfl_sync(0xFFFFFFFFu, (int)hv, run & 31) != 0;
-      if (!have_i) { ++n_wait; if (run == 0) __nanosleep(60); SP_T(1); continue; }      // its scout has not got there yet
-      if (__shfl_sync(0xFFFFFFFFu, (int)st, run & 31)) ++n_stale;
+      const bool fr = f < 32 ? fresh[0] : fresh[1];
+      if (!__shfl_sync(0xFFFFFFFFu, (int)fr, f & 31)) {
+        // no usable result in the registers: its scout may have written one since the window was loaded
+        const int4 rr = lds128(dyn_a + slot_i * 16u);
+        const bool hv = (((uint32_t)rr.z >> 21) & 0x3FFu) == ((((uint32_t)i >> 5) >> swd_shift) & 0x3FFu);
+        if (!hv) { ++n_wait; __nanosleep(40); SP_T(1); continue; }        // its scout has not got there yet
+        bool frs = !((uint32_t)rr.z & SPZ_NEVER);
+        if (frs) {
+#pragma unroll
+          for (int q = 0; q < K; ++q) frs = frs && lds32(chg_a + 4u * (uint32_t)lds32(rec_a + slot_i * RECB + (uint32_t)(lo_s + q) * 4u)) <= rr.w;
+        }
+        const unsigned long long T = ((unsigned long long)(uint32_t)rr.x << 32) | (uint32_t)rr.y;
+        if (frs && lex_lt(T, (uint32_t)rr.z & 0x1FFFu, B0k, B0p)) {     // it is sticky after all
+          if (lane == 0) {
+            dyn_smem[(acc_a - base_a) + slot_i] = (unsigned char)(0x80u | (((uint32_t)rr.z >> 13) & 0xFFu));
+            sts32v(front_a, i + 1);
+          }
+          ++i;
+          ++n_fast;
+          w = -128;                                                       // its neighbours may be new as well: reload the window
+          continue;
+        }
+        if (!((uint32_t)rr.z & SPZ_NEVER) && !frs) ++n_stale;
+      }
     }
     ++n_res;
     {
-      const uint32_t slot_i = ((((uint32_t)i >> 5) & swd_mask) << 5) | ((uint32_t)i & 31u);
       const uint32_t rb = rec_a + slot_i * RECB;
       if (lane == 0) dyn_smem[(acc_a - base_a) + slot_i] = 1;            // the leader writes this step's outcome itself
       const int4 hdr = lds128(rb + (uint32_t)SLP * 4u);               // meta, w_p, top, partition
@@ -743,7 +798,26 @@ __global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, 
       }
       const int32_t mycur = lane < n_cur ? lds32(rb + (uint32_t)(lo_s + (lane & 7)) * 4u) : -1;   // lane q: q-th current node
       const int32_t* Gt = G + (size_t)top * N;
-      while (lds32v(cdone_a) < i) { }                                     // nodeToNodeCounts holds every commit before step i
+      // nodeToNodeCounts[top] must hold every commit before step i.  The committer trails by a few hundred cycles;
+      // only an accepted step with the same top among the ones it has not reached yet makes the leader wait.
+      {
+        int cd = lds32v(cdone_a);
+        if (cd < i) {
+          bool clash = i - cd > 128;
+          for (int j0 = cd; j0 < i && !clash; j0 += 32) {
+            const int j = j0 + lane;
+            bool mine = false;
+            if (j < i) {
+              const uint32_t sj = ((((uint32_t)j >> 5) & swd_mask) << 5) | ((uint32_t)j & 31u);
+              mine = (dyn_smem[(acc_a - base_a) + sj] & 0x80u) && lds32(rec_a + sj * RECB + (uint32_t)(SLP + 2) * 4u) == top;
+            }
+            clash = __any_sync(0xFFFFFFFFu, mine);
+          }
+          if (clash) { ++n_cwait; while (lds32v(cdone_a) < i) { } }
+        }
+      }
+      bool retried = false;
+    resolve_again:
       bool resolved = false;
       int n_ch = 0;
       int32_t chosen[K];
@@ -752,64 +826,87 @@ __global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, 
       bool same = false;
       int reason = 0;
       if (row_clean && n_cur <= K) {
-        // candidates: my listed nodes (unless the row blocks them: current, or held by a higher-priority state)
-        // and, on lanes < n_cur, a current node
+        // Candidates: on lanes < n_cur a current node (with the stickiness), and my listed nodes unless a
+        // higher-priority state of the row holds them.  (A listed node that is also current needs no test: its
+        // listed key lacks the stickiness, so the current twin is picked first and takes the listed one with it -
+        // unless the stickiness is negative, then the state's own slots block too.)  The second list entry of
+        // every lane is only looked at when the K-th winner of the first round is not below lb1, a lower bound
+        // of all second entries.
+        const uint32_t blk = stick < 0.0 ? (slot_blocked | slot_state_s) : slot_blocked;
         unsigned long long ck[SP_LPL + 1];
         int32_t cnode[SP_LPL + 1];
-#pragma unroll
-        for (int u = 0; u < SP_LPL; ++u) {
-          cnode[u] = Ln[u];
-          ck[u] = ~0ull;
-#pragma unroll
-          for (int sl = 0; sl < 8; ++sl)
-            if (((slot_blocked >> sl) & 1u) && rowv[sl] == Ln[u]) cnode[u] = -1;
-        }
-        cnode[SP_LPL] = mycur;
-        ck[SP_LPL] = ~0ull;
-        int32_t gq[SP_LPL + 1];
-#pragma unroll
-        for (int u = 0; u <= SP_LPL; ++u) gq[u] = (cnode[u] >= 0 && have_p) ? ld_relaxed_gpu(Gt + cnode[u]) : 0;
         bool cur_ok = true;
+        auto eval = [&](int u) {                                        // exact key of candidate u (plan.go:634-689)
+          ck[u] = ~0ull;
+          if (u < SP_LPL) {
+            cnode[u] = Ln[u];
+            if (blk)
 #pragma unroll
-        for (int u = 0; u <= SP_LPL; ++u) {
+              for (int sl = 0; sl < 8; ++sl)
+                if (((blk >> sl) & 1u) && rowv[sl] == Ln[u]) cnode[u] = -1;
+          } else cnode[u] = mycur;
           if (cnode[u] >= 0) {
+            const int32_t g = have_p ? ld_relaxed_gpu(Gt + cnode[u]) : 0;
             const int4 ma = lds128(nd_a + (uint32_t)cnode[u] * 32u), mb = lds128(nd_a + (uint32_t)cnode[u] * 32u + 16u);
             const uint32_t fl = dyn_smem[(flg_a - base_a) + cnode[u]];
             if (u == SP_LPL && !(fl & NF_VALID)) cur_ok = false;
             ck[u] = sp_key(__hiloint2double(ma.y, ma.x), __hiloint2double(ma.w, ma.z), __hiloint2double(mb.y, mb.x),
-                           __hiloint2double(mb.w, mb.z), (fl & NF_BOOST) != 0, has_nw, gq[u], u == SP_LPL ? stick : 0.0, have_p, Pd, Py);
+                           __hiloint2double(mb.w, mb.z), (fl & NF_BOOST) != 0, has_nw, g, u == SP_LPL ? stick : 0.0, have_p, Pd, Py);
           }
-        }
+        };
+        eval(SP_LPL);
+        eval(0);
+#pragma unroll
+        for (int u = 1; u < SP_LPL; ++u) { cnode[u] = -1; ck[u] = ~0ull; }
         SP_T(2);
         if (__all_sync(0xFFFFFFFFu, cur_ok)) {
-          unsigned long long lastk = 0;
-          uint32_t lastp = 0;
-          bool hit_all = true;
-          for (int t = 0; t < K; ++t) {
-            unsigned long long bk = ~0ull;
-            uint32_t bp = 0xFFFFFFFFu;
+          const int32_t cnodeC = cnode[SP_LPL];
+          for (int round = 0; round < 2; ++round) {
+            unsigned long long lastk = 0;
+            uint32_t lastp = 0;
+            bool hit_all = true;
+            n_ch = 0;
+            uint32_t alive = 0;                                         // bit u: my candidate u is still in play
 #pragma unroll
-            for (int u = 0; u <= SP_LPL; ++u)
-              if (cnode[u] >= 0 && lex_lt(ck[u], (uint32_t)cnode[u], bk, bp)) { bk = ck[u]; bp = (uint32_t)cnode[u]; }
-            const Best b = warp_argmin_q(Best{(uint32_t)(bk >> 32), (uint32_t)bk, bp});
-            if (b.pos == 0xFFFFFFFFu) break;
-            chosen[t] = (int32_t)b.pos;
-            ++n_ch;
-            lastk = ((unsigned long long)b.hi << 32) | b.lo;
-            lastp = b.pos;
-            bool was_cur = false;
+            for (int u = 0; u <= SP_LPL; ++u) if (cnode[u] >= 0) alive |= 1u << u;
+            for (int t = 0; t < K; ++t) {
+              unsigned long long bk = ~0ull;
+              uint32_t bp = 0xFFFFFFFFu;
 #pragma unroll
-            for (int sl = 0; sl < 8; ++sl) was_cur = was_cur || (((slot_state_s >> sl) & 1u) && rowv[sl] == (int32_t)b.pos);
-            hit_all = hit_all && was_cur;
+              for (int u = 0; u <= SP_LPL; ++u)
+                if (((alive >> u) & 1u) && lex_lt(ck[u], (uint32_t)cnode[u], bk, bp)) { bk = ck[u]; bp = (uint32_t)cnode[u]; }
+              const Best b = warp_argmin_q(Best{(uint32_t)(bk >> 32), (uint32_t)bk, bp});
+              if (b.pos == 0xFFFFFFFFu) break;
+              chosen[t] = (int32_t)b.pos;
+              ++n_ch;
+              lastk = ((unsigned long long)b.hi << 32) | b.lo;
+              lastp = b.pos;
+              hit_all = hit_all && __any_sync(0xFFFFFFFFu, cnodeC == (int32_t)b.pos);
 #pragma unroll
-            for (int u = 0; u <= SP_LPL; ++u) if (cnode[u] == (int32_t)b.pos) cnode[u] = -1;
+              for (int u = 0; u <= SP_LPL; ++u) if (cnode[u] == (int32_t)b.pos) alive &= ~(1u << u);
+            }
+            // could an entry of the second column be among the first K?
+            if (round == 0 && SP_LPL > 1 && !(n_ch == K && lex_lt(lastk, lastp, lb1k, lb1p))) {
+#pragma unroll
+              for (int u = 1; u < SP_LPL; ++u) eval(u);
+              ++n_round2;
+              continue;
+            }
+            const bool complete = ubp == 0xFFFFFFFFu;                    // every live node is listed
+            if (n_ch == K) { resolved = complete || lex_lt(lastk, lastp, ubk, ubp); reason = 3; }
+            else { resolved = complete; reason = 2; }
+            same = resolved && hit_all && n_ch == n_cur && n_cur == K;
+            break;
           }
-          const bool complete = ubp == 0xFFFFFFFFu;                      // every live node is listed
-          if (n_ch == K) { resolved = complete || lex_lt(lastk, lastp, ubk, ubp); reason = 3; }
-          else { resolved = complete; reason = 2; }
-          same = resolved && hit_all && n_ch == n_cur && n_cur == K;
         } else reason = 1;
         SP_T(3);
+      }
+      if (!resolved && reason == 3 && movers_since_rebuild > 0 && !retried) {
+        // the K-th winner is not provably below every unlisted node: a fresh list usually settles it
+        retried = true;
+        rebuild_list();
+        SP_T(6);
+        goto resolve_again;
       }
       if (!resolved) {
         // ---- the team evaluates the step (and rebuilds the list if a count changed) ----------------------------------
@@ -826,7 +923,7 @@ __global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, 
           for (int t = 0; t < K; ++t) orec[t] = chosen[t];
           orec[K] = n_ch;
         }
-        if (!same) { adopt_list(); publish(false, 0, 0); ++n_mov; }
+        if (!same) { rebuild_list(); publish(false, 0, 0); ++n_mov; w = -64 - 64; }   // (stamps changed: reload the window)
         SP_T(6);
       } else {
         if (lane <= K) {                                               // outcome record: chosen[0..K), n_chosen
@@ -839,6 +936,7 @@ __global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, 
         if (!same) {
           // ---- a mover: lanes 0..n_cur-1 take the old nodes, lanes 8..8+n_ch-1 the new ones -------------------------
           ++n_mov;
+          ++movers_since_rebuild;
           const int32_t E1 = E + 1;
           const bool elig = n_cur == K;
           // A[top][x] changes by (x is chosen) - (the hypothesis counted x: eligible row and x current); a node whose
@@ -869,7 +967,7 @@ __global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, 
           if (is_new && again && !elig) { act = true; dA = 1; memb = 0; }      // kept node of a short row: only A moves
           act = act && x >= 0;
           unsigned long long nk = ~0ull;
-          bool ins = false;
+          bool tvalid = false;
           if (act) {
             const int4 ma = lds128(nd_a + (uint32_t)x * 32u), mb = lds128(nd_a + (uint32_t)x * 32u + 16u);
             const uint32_t fl = dyn_smem[(flg_a - base_a) + x];
@@ -889,66 +987,30 @@ __global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, 
             double* nd = reinterpret_cast<double*>(dyn_smem) + 4 * (size_t)x;
             nd[0] = cd; nd[1] = ff;
             sts32(chg_a + 4u * (uint32_t)x, E1);
-            nk = sp_key(cd, ff, __hiloint2double(mb.y, mb.x), __hiloint2double(mb.w, mb.z), (fl & NF_BOOST) != 0, has_nw, 0, 0.0, have_p, Pd, Py);
-            ins = (fl & NF_VALID) && lex_lt(nk, (uint32_t)x, ubk, ubp);
+            nk = sp_base_key(cd, ff, __hiloint2double(mb.y, mb.x), __hiloint2double(mb.w, mb.z), (fl & NF_BOOST) != 0, has_nw);
+            *reinterpret_cast<unsigned long long*>(dyn_smem + (bk_a - base_a) + 8u * (uint32_t)x) = nk;
+            tvalid = (fl & NF_VALID) != 0;
           }
           SP_T(4);
-          // list: a touched node that is listed keeps its place with its new key, or leaves when the key is no
-          // longer below ub; a touched node that is not listed and is below ub needs a free place
+          // list: every touched node goes to its owner lane (new key in place, listed if it fell below the lane's
+          // bound); window results computed from its old state are dropped
           const uint32_t actm = __ballot_sync(0xFFFFFFFFu, act);
-          bool placed_me = false;
           for (uint32_t m = actm; m; m &= m - 1u) {
             const int src = __ffs(m) - 1;
             const int32_t tx = __shfl_sync(0xFFFFFFFFu, x, src);
             const unsigned long long tk = __shfl_sync(0xFFFFFFFFu, nk, src);
-            const bool tins = __shfl_sync(0xFFFFFFFFu, (int)ins, src) != 0;
-            bool mine = false;
+            const bool tv = __shfl_sync(0xFFFFFFFFu, (int)tvalid, src) != 0;
+            list_touch(tx, tk, tv);
 #pragma unroll
-            for (int u = 0; u < SP_LPL; ++u)
-              if (Ln[u] == tx) {
-                mine = true;
-                if (tins) Lk[u] = tk; else { Ln[u] = -1; Lk[u] = ~0ull; }
-              }
-            const bool listed = __any_sync(0xFFFFFFFFu, mine);
-            if (lane == src && listed) placed_me = true;
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+              for (int q = 0; q < K; ++q) if (cn[u][q] == tx) fresh[u] = false;
           }
-          const uint32_t insm = __ballot_sync(0xFFFFFFFFu, ins && !placed_me);
-          const int n_ins = __popc(insm);
-          if (n_ins) {
-            if (ins && !placed_me) ctl.ins[__popc(insm & ((1u << lane) - 1u))] = make_uint4((uint32_t)(nk >> 32), (uint32_t)nk, (uint32_t)x, 0u);
-            __syncwarp();
-            int placed = 0;
-#pragma unroll
-            for (int u = 0; u < SP_LPL; ++u) {
-              const uint32_t freem = __ballot_sync(0xFFFFFFFFu, Ln[u] < 0);
-              const int r2 = placed + __popc(freem & ((1u << lane) - 1u));
-              if (Ln[u] < 0 && r2 < n_ins) {
-                const uint4 e = ctl.ins[r2];
-                Lk[u] = ((unsigned long long)e.x << 32) | e.y;
-                Ln[u] = (int32_t)e.z;
-              }
-              placed += __popc(freem);
-            }
-            for (int r2 = placed; r2 < n_ins; ++r2) {                  // no room: the node stays unlisted, ub covers it
-              const uint4 e = ctl.ins[r2];
-              const unsigned long long k = ((unsigned long long)e.x << 32) | e.y;
-              if (lex_lt(k, e.z, ubk, ubp)) { ubk = k; ubp = e.z; }
-            }
-            __syncwarp();
-          }
-          int occ = 0;
-#pragma unroll
-          for (int u = 0; u < SP_LPL; ++u) occ += __popc(__ballot_sync(0xFFFFFFFFu, Ln[u] >= 0));
           publish(act && dA != 0 && have_p, (int32_t)((size_t)top * N + (x < 0 ? 0 : x)), dA);
-          if (occ < SP_LMIN && ubp != 0xFFFFFFFFu) {
-            SP_T(5);
-            team_cmd(SP_OP_REBUILD, 0);                                 // reads the mirror only
-            adopt_list();
-            SP_T(6);
-          } else {
-            recompute_b0();
-            SP_T(5);
-          }
+          recompute_b0();
+          // a list whose smallest key is no longer below ub has lost its grip on the minimum: scan the base keys again
+          if (b0_clamped && ubp != 0xFFFFFFFFu && movers_since_rebuild >= 4) { SP_T(5); rebuild_list(); SP_T(6); }
+          else SP_T(5);
         }
       }
       ++i;
@@ -966,6 +1028,8 @@ __global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, 
     cyc[7] = clock64() - t_begin;
     for (int x = 0; x < 8; ++x) D.spec_cyc[x] += cyc[x];
     for (int x = 0; x < 4; ++x) D.spec_why[x] += why[x];
+    D.spec_cwait += n_cwait;
+    D.spec_round2 += n_round2;
   }
 #undef SP_T
 }

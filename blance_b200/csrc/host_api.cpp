@@ -3,6 +3,7 @@
 #include "host_api.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -849,18 +850,26 @@ PartitionMap PlanNextMapEx(PartitionMap& prevMap, PartitionMap& partitionsToAssi
                            const PartitionModel& model, const PlanNextMapOptions& options,
                            Warnings* warnings, PlanStats* stats) {
   if (warnings) warnings->clear();
+  using clk = std::chrono::steady_clock;
+  auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+  const auto t0 = clk::now();
   auto ip = InternPlan(prevMap, partitionsToAssign, nodesAll, nodesToRemove, nodesToAdd, model, options);
   PlanOutBuffers ob(*ip);
+  const auto t1 = clk::now();
   blance_ctx* ctx = DefaultContext();
   int st = blance_plan_next_map(ctx, &ip->in, &ob.out);
   if (st != BLANCE_OK) throw BlanceError(st, std::string("blance_plan_next_map failed: ") + blance_last_error(ctx));
+  const auto t2 = clk::now();
   if (stats) {
     stats->iters_run = ob.out.iters_run; stats->converged = ob.out.converged; stats->steps = ob.out.steps;
     stats->device_ms = ob.out.device_ms; stats->kernel_ms = ob.out.kernel_ms; stats->pass_ms = ob.out.pass_ms;
+    stats->intern_ms = ms(t0, t1); stats->call_ms = ms(t1, t2);
   }
   if (ob.out.iters_run <= 0) return PartitionMap{};                  // MaxIterationsPerPlan <= 0: plan.go:32,57
   PartitionMap next = UninternPlan(*ip, ob, warnings);
+  const auto t3 = clk::now();
   if (ob.out.iters_run >= 2 || !ob.out.converged) ReplayCallerMutation(next, prevMap, partitionsToAssign);
+  if (stats) { stats->unintern_ms = ms(t2, t3); stats->mutate_ms = ms(t3, clk::now()); }
   return next;
 }
 

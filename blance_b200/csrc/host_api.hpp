@@ -81,6 +81,8 @@ struct PlanStats {                     // not in the reference; what the GPU did
   int converged = 0;
   int64_t steps = 0;
   float device_ms = 0, kernel_ms = 0, pass_ms = 0;
+  // host wall time of the stages of PlanNextMapEx: maps -> tables, the C ABI call, tables -> map, plan.go:49-52
+  double intern_ms = 0, call_ms = 0, unintern_ms = 0, mutate_ms = 0;
 };
 
 // api.go:147-157.  prevMap and partitionsToAssign are mutated as plan.go:49-52

@@ -7,6 +7,7 @@
 // the flat tables (and the address of the blance_plan_in / blance_plan_out structs)
 // so that tests can hand the very same tables to the CPU oracle via ctypes.
 #include <pybind11/numpy.h>
+#include <chrono>
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
@@ -123,6 +124,93 @@ PYBIND11_MODULE(_host, m) {
       py::arg("node_weights") = py::none(), py::arg("node_hierarchy") = py::none(),
       py::arg("hierarchy_rules") = py::none(), py::arg("booster") = 0, py::arg("max_iterations") = 10,
       py::arg("engine") = 0);
+
+  // The string API end to end on a large synthetic cluster, without Python dicts in the way: the PartitionMap is
+  // built here from flat rows with the naming recipe of blance_b200/synth.py (nodes "n%04d", partitions decimal,
+  // states primary / replica / standby) - that is set-up, untimed - then PlanNextMapEx runs on it exactly as a Go
+  // host would call it (maps of strings in, map of strings out, caller maps mutated).  Returns the stage times
+  // and the next map turned back into rows so the caller can compare it with the flat path.
+  m.def("bench_string_api", [](py::array_t<int32_t, py::array::c_style | py::array::forcecast> rows, int n_nodes,
+                               std::vector<int> constraints, std::vector<int> removed, std::vector<int> added,
+                               std::optional<py::array_t<int32_t, py::array::c_style | py::array::forcecast>> node_weights,
+                               std::optional<py::array_t<int32_t, py::array::c_style | py::array::forcecast>> part_weight,
+                               std::optional<py::array_t<uint8_t, py::array::c_style | py::array::forcecast>> part_has_weight,
+                               std::optional<std::vector<int>> state_stickiness, int max_iterations) {
+    static const char* kStates[] = {"primary", "replica", "standby"};
+    const auto rb = rows.unchecked<2>();
+    const ssize_t P = rb.shape(0), SL = rb.shape(1);
+    const int S = (int)constraints.size();
+    if (S > 3) throw std::runtime_error("bench_string_api: at most 3 states");
+    Strs nodes((size_t)n_nodes);
+    for (int i = 0; i < n_nodes; ++i) { char b[16]; std::snprintf(b, sizeof b, "n%04d", i); nodes[(size_t)i] = b; }
+    PartitionModel model;
+    for (int s = 0; s < S; ++s) model[kStates[s]] = PartitionModelState{s, constraints[(size_t)s]};
+    PartitionMap prev;
+    prev.reserve((size_t)P);
+    for (ssize_t p = 0; p < P; ++p) {
+      Partition part;
+      part.Name = std::to_string(p);
+      ssize_t slot = 0;
+      for (int s = 0; s < S; ++s) {
+        Strs l;
+        for (int j = 0; j < constraints[(size_t)s]; ++j, ++slot)
+          if (slot < SL && rb(p, slot) >= 0) l.push_back(nodes[(size_t)rb(p, slot)]);
+        part.NodesByState[kStates[s]] = std::move(l);
+      }
+      prev.emplace(part.Name, std::move(part));
+    }
+    PlanNextMapOptions o;
+    o.MaxIterationsPerPlan = max_iterations;
+    if (node_weights) {
+      o.NodeWeights.emplace();
+      const auto w = node_weights->unchecked<1>();
+      for (int i = 0; i < n_nodes; ++i) (*o.NodeWeights)[nodes[(size_t)i]] = w(i);
+    }
+    if (part_weight && part_has_weight) {
+      o.PartitionWeights.emplace();
+      const auto w = part_weight->unchecked<1>();
+      const auto h = part_has_weight->unchecked<1>();
+      for (ssize_t p = 0; p < P; ++p) if (h(p)) (*o.PartitionWeights)[std::to_string(p)] = w(p);
+    }
+    if (state_stickiness) {
+      o.StateStickiness.emplace();
+      for (int s = 0; s < S && s < (int)state_stickiness->size(); ++s) (*o.StateStickiness)[kStates[s]] = (*state_stickiness)[(size_t)s];
+    }
+    Strs rm, ad;
+    for (int i : removed) rm.push_back(nodes[(size_t)i]);
+    for (int i : added) ad.push_back(nodes[(size_t)i]);
+    Warnings warnings;
+    PlanStats stats;
+    PartitionMap next;
+    double total_ms;
+    {
+      py::gil_scoped_release rel;
+      const auto t0 = std::chrono::steady_clock::now();
+      next = PlanNextMapEx(prev, prev, nodes, OptStrs(rm), OptStrs(ad), model, o, &warnings, &stats);   // the same map twice, as blance's callers do
+      total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    py::array_t<int32_t> out({P, SL});
+    auto ob = out.mutable_unchecked<2>();
+    for (ssize_t p = 0; p < P; ++p) for (ssize_t j = 0; j < SL; ++j) ob(p, j) = -1;
+    for (const auto& kv : next) {
+      const ssize_t p = std::stoll(kv.first);
+      ssize_t slot = 0;
+      for (int s = 0; s < S; ++s) {
+        auto it = kv.second.NodesByState.find(kStates[s]);
+        if (it != kv.second.NodesByState.end() && it->second)
+          for (size_t j = 0; j < it->second->size() && (int)j < constraints[(size_t)s]; ++j) ob(p, slot + (ssize_t)j) = std::atoi((*it->second)[j].c_str() + 1);
+        slot += constraints[(size_t)s];
+      }
+    }
+    py::dict d;
+    d["total_ms"] = total_ms; d["intern_ms"] = stats.intern_ms; d["call_ms"] = stats.call_ms;
+    d["unintern_ms"] = stats.unintern_ms; d["mutate_ms"] = stats.mutate_ms; d["device_ms"] = stats.device_ms;
+    d["iterations"] = stats.iters_run; d["steps"] = stats.steps; d["next_rows"] = out; d["warnings"] = (int)warnings.size();
+    d["host_threads"] = HostThreads();
+    return d;
+  }, py::arg("rows"), py::arg("n_nodes"), py::arg("constraints"), py::arg("removed"), py::arg("added"),
+     py::arg("node_weights") = py::none(), py::arg("part_weight") = py::none(), py::arg("part_has_weight") = py::none(),
+     py::arg("state_stickiness") = py::none(), py::arg("max_iterations") = 10);
 
   m.def("CalcPartitionMoves", [](const Strs& states, const NodesByState& beg, const NodesByState& end, bool favor) {
     std::vector<std::tuple<std::string, std::string, std::string>> out;

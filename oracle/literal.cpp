@@ -278,6 +278,16 @@ InnerResult plan_next_map_inner(const PartitionMap& prev_map, const PartitionMap
   }
   {
     PartitionSorter by_name;   // stateName "", no prevMap/add/remove/weights
+    if (opts.memoize_partition_scores) {
+      std::vector<std::pair<std::vector<std::string>, PartitionPtr>> keyed;
+      keyed.reserve(next_partitions.size());
+      for (auto& p : next_partitions) keyed.emplace_back(by_name.score(*p), p);
+      std::sort(keyed.begin(), keyed.end(), [](const auto& a, const auto& b) {
+        if (a.first != b.first) return a.first < b.first;
+        return a.second->name < b.second->name;
+      });
+      for (size_t x = 0; x < next_partitions.size(); ++x) next_partitions[x] = keyed[x].second;
+    } else
     std::sort(next_partitions.begin(), next_partitions.end(),
               [&](const PartitionPtr& a, const PartitionPtr& b) { return by_name.less(*a, *b); });
   }
@@ -406,6 +416,16 @@ InnerResult plan_next_map_inner(const PartitionMap& prev_map, const PartitionMap
     ps.nodes_to_add = &nodes_to_add;
     ps.partition_weights = &opts.partition_weights;
     std::vector<PartitionPtr> order = next_partitions;
+    if (opts.memoize_partition_scores) {
+      std::vector<std::pair<std::vector<std::string>, PartitionPtr>> keyed;
+      keyed.reserve(order.size());
+      for (auto& p : order) keyed.emplace_back(ps.score(*p), p);
+      std::sort(keyed.begin(), keyed.end(), [](const auto& a, const auto& b) {
+        if (a.first != b.first) return a.first < b.first;            // element-wise, then by length: plan.go:498-511
+        return a.second->name < b.second->name;
+      });
+      for (size_t x = 0; x < order.size(); ++x) order[x] = keyed[x].second;
+    } else
     std::sort(order.begin(), order.end(),
               [&](const PartitionPtr& a, const PartitionPtr& b) { return ps.less(*a, *b); });
 

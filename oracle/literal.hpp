@@ -70,6 +70,10 @@ struct Options {                         // api.go:183-190 (+ the package-level 
   // reference arm: every slice is one bounded sample of the workload; the copies and sorts around the passes are
   // outside the slices).  slice_seconds receives one entry per completed slice.  Not part of the reference.
   int64_t slice_steps = 0;
+  // Evaluate partitionSorter.Score once per partition and sort the precomputed keys instead of recomputing the
+  // two Sprintf strings inside every comparison (plan.go:495-562).  Same order (Score is a function of the
+  // partition alone during a sort); only bench.py's reference arm sets it, to keep its untimed set-up short.
+  bool memoize_partition_scores = false;
   std::vector<double>* slice_seconds = nullptr;
 };
 

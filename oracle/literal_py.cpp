@@ -68,12 +68,13 @@ PYBIND11_MODULE(_literal, m) {
          const std::optional<IntMap>& msc, const std::optional<IntMap>& pw, const std::optional<IntMap>& ss,
          const std::optional<IntMap>& nw, const std::optional<StrMap>& nh,
          const std::optional<std::unordered_map<std::string, std::vector<std::pair<int64_t, int64_t>>>>& hr,
-         int booster, int max_iterations, int64_t max_steps_per_pass, int64_t slice_steps) {
+         int booster, int max_iterations, int64_t max_steps_per_pass, int64_t slice_steps, bool memoize_partition_scores) {
         PartitionModel pm;
         for (const auto& kv : model) pm[kv.first] = {kv.second.first, kv.second.second};
         Options o = make_options(msc, pw, ss, nw, nh, hr, booster, max_iterations, max_steps_per_pass);
         std::vector<double> slices;
         o.slice_steps = slice_steps;
+        o.memoize_partition_scores = memoize_partition_scores;
         if (slice_steps > 0) o.slice_seconds = &slices;
         PartitionMap prev_map = to_map(prev);
         PartitionMap assign_map;
@@ -104,7 +105,8 @@ PYBIND11_MODULE(_literal, m) {
       py::arg("partition_weights") = py::none(), py::arg("state_stickiness") = py::none(),
       py::arg("node_weights") = py::none(), py::arg("node_hierarchy") = py::none(),
       py::arg("hierarchy_rules") = py::none(), py::arg("booster") = 0, py::arg("max_iterations") = 10,
-      py::arg("max_steps_per_pass") = -1, py::arg("slice_steps") = 0);
+      py::arg("max_steps_per_pass") = -1, py::arg("slice_steps") = 0,
+      py::arg("memoize_partition_scores") = false);
 
   m.def("calc_partition_moves",
         [](const Strs& states, const NodesByState& beg, const NodesByState& end, bool favor_min_nodes) {

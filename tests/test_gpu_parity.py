@@ -202,6 +202,18 @@ def two_stage(ctx, cfg, P=None, engine=0):
     return got2
 
 
+@pytest.mark.parametrize("N", [1500, 3000, 6000])
+def test_many_nodes_every_engine(ctx, N):
+    """Clusters with more than 1 024 nodes (4, 8 and 16 nodes per thread in the lock-step / sequencer kernels, the team
+    evaluation of the speculative kernel up to 2 048): rebalance with weights and stickiness, every engine against the
+    oracle."""
+    t = synth.make_rebalance(4, P=6144, N=N)
+    ref = oracle_tables(t)
+    for engine in (0, 1, 2):
+        t.engine = engine
+        assert_same(ctx.plan_next_map(t), ref)
+
+
 def test_cfg1_64x8(ctx):
     two_stage(ctx, 1)
 
@@ -299,6 +311,37 @@ def test_batch_equals_individual(ctx):
     refs2 = [oracle_tables(t) for t in ts2]
     for g, r in zip(ctx.plan_next_map_batch(ts2), refs2):
         assert_same(g, r)
+
+
+def test_wide_batch_every_instance_vs_oracle(ctx):
+    """160 instances in one batch: more CTAs than half the SMs, so the pass kernels run in their narrow
+    configuration (4 scouts per CTA / one sequencer warp) - the path BASELINE config 5 takes.  Every instance is
+    compared with the oracle, for the default engine and for round 1's sequencer kernel."""
+    fresh = [synth.make_fresh(5, seed_offset=i, P=96 + 4 * (i % 40)) for i in range(160)]
+    got = ctx.plan_next_map_batch(fresh)
+    for g, t in zip(got, fresh):
+        assert_same(g, oracle_tables(t))
+    for engine in (0, 2):
+        rebs = [synth.make_rebalance(5, g.next_rows, seed_offset=i, P=96 + 4 * (i % 40)) for i, g in enumerate(got)]
+        for t in rebs:
+            t.engine = engine
+        for g, t in zip(ctx.plan_next_map_batch(rebs), rebs):
+            assert_same(g, oracle_tables(t))
+
+
+def test_multi_device_context_shards_a_batch():
+    """blance_ctx_create_multi: the batch is spread over every visible GPU (instance i -> device i mod G); results
+    must not depend on where an instance ran.  With one visible GPU this still exercises the dispatch code."""
+    import torch
+    G = max(1, min(8, torch.cuda.device_count()))
+    mctx = tables.Context(device_ids=list(range(G)))
+    assert mctx.device_count() == G
+    ts = [synth.make_rebalance(4, P=512 + 64 * i, N=96) for i in range(2 * G + 1)]
+    for g, t in zip(mctx.plan_next_map_batch(ts), ts):
+        assert_same(g, oracle_tables(t))
+    # single-plan entry points of a multi-device context run on its first device
+    assert_same(mctx.plan_next_map(ts[0]), oracle_tables(ts[0]))
+    mctx.close()
 
 
 def test_resident_plan_replay(ctx):
