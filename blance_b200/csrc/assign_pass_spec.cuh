@@ -58,6 +58,7 @@ struct SpecCtl {
   alignas(8) unsigned long long mbar[32 * SP_D];
   int32_t epoch, front, cmd_seq, cmd_op, cmd_arg, cmd_epoch;
   int32_t pub_head, pub_done, pub_quit, commit_done;
+  int32_t abort_flag;                // a wait loop gave up (never in a correct run): every role leaves, the host reports an error
   int32_t res_n, res_same;
   int32_t res_chosen[BL_K_MAX];
 };
@@ -213,6 +214,7 @@ __global__ void __launch_bounds__(448, 1) k_assign_pass_spec(DPool pool, int s, 
   const uint32_t pubd_a = ctl_a + (uint32_t)offsetof(SpecCtl, pub_done);
   const uint32_t pubx_a = ctl_a + (uint32_t)offsetof(SpecCtl, pub_quit);
   const uint32_t cdone_a = ctl_a + (uint32_t)offsetof(SpecCtl, commit_done);
+  const uint32_t abort_a = ctl_a + (uint32_t)offsetof(SpecCtl, abort_flag);
 
   // ---- pass constants, mirror, ring ------------------------------------------------------------------
   for (int i = atid; i < SLP; i += NTA) {
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(448, 1) k_assign_pass_spec(DPool pool, int s, 
   if (atid == 0) {
     for (int i = 0; i < SWD; ++i) mbar_init(mbar_a + 8u * i, 1);
     ctl.epoch = 0; ctl.front = 0; ctl.cmd_seq = 0; ctl.cmd_op = 0; ctl.cmd_arg = 0; ctl.cmd_epoch = 0;
-    ctl.pub_head = 0; ctl.pub_done = 0; ctl.pub_quit = 0; ctl.commit_done = 0;
+    ctl.pub_head = 0; ctl.pub_done = 0; ctl.pub_quit = 0; ctl.commit_done = 0; ctl.abort_flag = 0;
     ctl.res_n = 0; ctl.res_same = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -592,6 +594,21 @@ __global__ void __launch_bounds__(448, 1) k_assign_pass_spec(DPool pool, int s, 
 #define SP_T(ix) do { } while (0)
 #endif
 
+  // Watchdog of the leader's wait loops: a correct run never gets near the limit; if one does, say where and stop
+  // the pass (the plan then fails with BLANCE_ERR_CUDA instead of hanging the GPU).
+  long long spins = 0;
+  auto stuck = [&](int where, int a, int b) {
+    if (++spins < (1ll << 26)) return false;
+    if (lane == 0) {
+      printf("[blance] speculative pass stuck (wait %d) at step %d of %d: %d %d | front %d commit_done %d epoch %d pub %d/%d\n", where, a, n_assign, b, 0,
+             *(volatile int32_t*)&ctl.front, *(volatile int32_t*)&ctl.commit_done, *(volatile int32_t*)&ctl.epoch,
+             *(volatile int32_t*)&ctl.pub_done, *(volatile int32_t*)&ctl.pub_head);
+      sts32v(abort_a, 1);
+      D.spec_abort = 1;
+    }
+    return true;
+  };
+  bool aborted = false;
   auto team_cmd = [&](int op, int arg) {
     if (lane == 0) {
       *(volatile int32_t*)&ctl.cmd_op = op;
@@ -675,7 +692,12 @@ __global__ void __launch_bounds__(448, 1) k_assign_pass_spec(DPool pool, int s, 
         const int32_t n = Ln[0]; Ln[0] = Ln[1]; Ln[1] = n;
       } else if (Ln[0] < 0 && Ln[1] >= 0) { Lk[0] = Lk[1]; Ln[0] = Ln[1]; Lk[1] = ~0ull; Ln[1] = -1; }
     }
-    if (tvalid && lex_lt(tk, (uint32_t)tx, lb1k, lb1p)) { lb1k = tk; lb1p = (uint32_t)tx; }   // lb1 only has to be a lower bound
+    // lb1 bounds the second-column entries from below: it moves when the node sits there now with a smaller key
+    if (__any_sync(0xFFFFFFFFu, (tx & 31) == lane && Ln[1] >= 0 && lex_lt(Lk[1], (uint32_t)Ln[1], lb1k, lb1p))) {
+      const int o = tx & 31;
+      lb1k = __shfl_sync(0xFFFFFFFFu, Lk[1], o);
+      lb1p = (uint32_t)__shfl_sync(0xFFFFFFFFu, Ln[1], o);
+    }
     if (__any_sync(0xFFFFFFFFu, ub_moved)) recompute_ub();
   };
   // Hands epoch E + 1 to the publisher: the A updates of the lanes with `has`, then the marker that lets it
@@ -684,7 +706,7 @@ __global__ void __launch_bounds__(448, 1) k_assign_pass_spec(DPool pool, int s, 
   auto publish = [&](bool has, int32_t idx, int32_t dA) {
     const uint32_t m = __ballot_sync(0xFFFFFFFFu, has);
     const int n = __popc(m) + 1;
-    while (pub_head + n - lds32v(pubd_a) > 64) __nanosleep(20);
+    while (pub_head + n - lds32v(pubd_a) > 64) { __nanosleep(20); if (stuck(1, pub_head, n)) { aborted = true; break; } }
     if (has) sts128(pubq_a + 16u * (uint32_t)((pub_head + __popc(m & ((1u << lane) - 1u))) & 63), (uint32_t)idx, (uint32_t)dA, (uint32_t)(E + 1), 0u);
     if (lane == 0) sts128(pubq_a + 16u * (uint32_t)((pub_head + n - 1) & 63), 0xFFFFFFFFu, 0u, (uint32_t)(E + 1), 1u);
     pub_head += n;
@@ -749,6 +771,7 @@ __global__ void __launch_bounds__(448, 1) k_assign_pass_spec(DPool pool, int s, 
     i = w + f;
     __syncwarp();
     if (f > done && lane == 0) sts32v(front_a, i);
+    if (aborted) break;
     if (f == 64 || i >= n_assign) continue;
     SP_T(0);
     // ---- step i was not accepted -----------------------------------------------------------------------------------
@@ -759,7 +782,12 @@ __global__ void __launch_bounds__(448, 1) k_assign_pass_spec(DPool pool, int s, 
         // no usable result in the registers: its scout may have written one since the window was loaded
         const int4 rr = lds128(dyn_a + slot_i * 16u);
         const bool hv = (((uint32_t)rr.z >> 21) & 0x3FFu) == ((((uint32_t)i >> 5) >> swd_shift) & 0x3FFu);
-        if (!hv) { ++n_wait; __nanosleep(40); SP_T(1); continue; }        // its scout has not got there yet
+        if (!hv) {                                                        // its scout has not got there yet
+          ++n_wait; __nanosleep(40); SP_T(1);
+          if (stuck(2, i, (int)rr.z)) { aborted = true; break; }
+          continue;
+        }
+        spins = 0;
         bool frs = !((uint32_t)rr.z & SPZ_NEVER);
         if (frs) {
 #pragma unroll
@@ -813,7 +841,7 @@ __global__ void __launch_bounds__(448, 1) k_assign_pass_spec(DPool pool, int s, 
             }
             clash = __any_sync(0xFFFFFFFFu, mine);
           }
-          if (clash) { ++n_cwait; while (lds32v(cdone_a) < i) { } }
+          if (clash) { ++n_cwait; while (lds32v(cdone_a) < i) { if (stuck(3, i, cd)) { aborted = true; break; } } spins = 0; }
         }
       }
       bool retried = false;

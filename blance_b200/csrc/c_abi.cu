@@ -767,6 +767,8 @@ static int fetch(blance_ctx* ctx, blance_plan* pl, blance_plan_out* outs) {
   std::vector<DInst> fin(n);
   CK(cudaMemcpyAsync(fin.data(), pl->pool.insts, sizeof(DInst) * (size_t)n, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  for (int i = 0; i < n; ++i)
+    if (fin[i].spec_abort) return fail(ctx, BLANCE_ERR_CUDA, "the speculative pass kernel gave up waiting (internal error; see stderr of the device printf)");
   if (getenv("BLANCE_SPEC_STATS"))
     for (int i = 0; i < n && i < 4; ++i)
       std::fprintf(stderr, "[blance] inst %d: steps %lld accepted %lld | resolved by the leader %lld (stale results %lld) movers %lld team %lld rebuilds %lld waits %lld\n",

@@ -58,6 +58,7 @@ struct DInst {
   // counters of the speculative kernel (whole plan)
   long long spec_resolved, spec_movers, spec_team, spec_rebuilds, spec_waits, spec_stale;
   long long spec_cyc[8];   // leader cycles: scans | waits | resolve loads+keys | resolve picks | mover mirror | mover list+publish | team | passes
+  long long spec_abort;    // the speculative kernel's watchdog fired (a bug: the plan is reported as failed)
   long long spec_round2;   // resolves that had to look at the second list column
   long long spec_cwait;    // resolves that had to wait for the committer (a pending commit shared their top node)
   long long spec_why[4];   // team evaluations by cause: row not clean | current node dead | candidates ran out | bound test failed

@@ -10,7 +10,11 @@
 //   PlanNextMapEx       api.go:147-157  ->  planNextMapExB200      ->  blance_plan_next_map
 //   CalcPartitionMoves  moves.go:41-119 ->  calcPartitionMovesB200 ->  blance_calc_partition_moves
 //
-// There is no CPU fallback by design: a non-zero status panics with blance_last_error().
+// Inside libblance_b200 there is no CPU fallback.  This shim lives in the same package as the Go planner, so the
+// inputs the device path reports as BLANCE_ERR_UNSUPPORTED (more than 8 states, 32 slots, 8192 nodes, 16
+// constraints; a CustomNodeSorter; Partition.Name != key ...) and a missing / failed device (BLANCE_ERR_CUDA) go
+// to the package's own planNextMapEx / calcPartitionMovesGo - a drop-in must not turn valid inputs into panics.
+// BLANCE_ERR_INVALID_ARG still panics: the reference panics (or misbehaves) on those inputs too.
 
 //go:build cgo
 
@@ -151,7 +155,8 @@ func planNextMapExB200(prevMap, partitionsToAssign PartitionMap,
 	// plan.go:580: an application that replaced the sorter keeps the Go planner (func values only compare
 	// through reflect)
 	if reflect.ValueOf(CustomNodeSorter).Pointer() != reflect.ValueOf(defaultNodeSorter).Pointer() {
-		panic("blance_b200: CustomNodeSorter cannot cross the C ABI") // BLANCE_ERR_UNSUPPORTED
+		// a func value cannot cross the C ABI (BLANCE_ERR_UNSUPPORTED): the Go planner keeps this call
+		return planNextMapEx(prevMap, partitionsToAssign, nodesAll, nodesToRemove, nodesToAdd, model, opts)
 	}
 	var ar cArena
 	defer ar.free()
@@ -265,11 +270,12 @@ func planNextMapExB200(prevMap, partitionsToAssign PartitionMap,
 	fill := func(m PartitionMap, rows []int32, shape []uint8, present []uint8, isPrev bool) {
 		for name, p := range m {
 			pi := partID[name]
-			present[pi] = 1
+			present[pi] |= 1
 			for sn, list := range p.NodesByState {
 				s, ok := stateID[sn]
 				if !ok {
 					if isPrev {
+						present[pi] = 3 // bit 1: a key outside the model, reflect.DeepEqual never matches it (plan.go:38)
 						for _, n := range list {
 							extras = append(extras, extra{int32(pi), nodes.get(n)})
 						}
@@ -421,6 +427,10 @@ func planNextMapExB200(prevMap, partitionsToAssign PartitionMap,
 	out.next_rows, out.next_shape, out.warn = pNext, pNextShape, pWarn
 
 	if st := C.blance_plan_next_map(b200(), &in, &out); st != C.BLANCE_OK {
+		if st == C.BLANCE_ERR_UNSUPPORTED || st == C.BLANCE_ERR_CUDA || st == C.BLANCE_ERR_NOMEM {
+			// nothing was mutated yet: the Go planner answers (same results, only slower)
+			return planNextMapEx(prevMap, partitionsToAssign, nodesAll, nodesToRemove, nodesToAdd, model, opts)
+		}
 		panic("blance_b200: " + C.GoString(C.blance_last_error(b200())))
 	}
 	if out.iters_run <= 0 { // MaxIterationsPerPlan <= 0: plan.go:32,57
@@ -535,3 +545,124 @@ func calcPartitionMovesB200(states []string, beg, end map[string][]string, favor
 	}
 	return ops
 }
+
+// seedNextMovesB200 replaces the loop of orchestrate.go:273-287: CalcPartitionMoves for EVERY partition of
+// begMap in one device call (blance_moves_create), returned as the map of *NextMoves the orchestrator keeps.
+// One partition at a time (calcPartitionMovesB200 above) costs a launch and a round trip per partition and is
+// slower than the Go function it replaces; this batched form is the one to wire in.  The returned handle stays
+// valid until blance_moves_free and answers findAvailableMovesUnlocked (orchestrate.go:749-763) and the
+// FindMoveFunc's pick (orchestrate.go:177-186) for a vector of cursors with blance_moves_available - see
+// availableMovesB200.  UNTESTED GO, like the rest of this file; the C ABI underneath is covered by
+// tests/test_gpu_parity.py::test_moves_plan_csr_and_available_moves.
+type movesB200 struct {
+	h         *C.blance_moves
+	partNames []string // partition index -> name (sorted: the fixed order that replaces Go's map order)
+	nodeNames []string
+	nNodeIDs  int
+}
+
+func seedNextMovesB200(states []string, begMap, endMap PartitionMap, favorMinNodes bool) (map[string]*NextMoves, *movesB200) {
+	partNames := make([]string, 0, len(begMap))
+	for name := range begMap {
+		partNames = append(partNames, name)
+	}
+	sort.Strings(partNames)
+	nodes := &interner{ids: map[string]int32{}}
+	// slot layout: the visited states first, every list as wide as the longest one of that state
+	S := len(states)
+	width := make([]int, S)
+	for _, name := range partNames {
+		for i, s := range states {
+			if w := len(begMap[name].NodesByState[s]); w > width[i] {
+				width[i] = w
+			}
+			if e := endMap[name]; e != nil {
+				if w := len(e.NodesByState[s]); w > width[i] {
+					width[i] = w
+				}
+			}
+		}
+	}
+	var ar cArena
+	defer ar.free()
+	pOff, off := ar.i32(S+1, 0)
+	for i := range states {
+		off[i+1] = off[i] + int32(width[i])
+	}
+	SL, P := int(off[S]), len(partNames)
+	pBeg, begRows := ar.i32(P*SL, C.BLANCE_NO_NODE)
+	pEnd, endRows := ar.i32(P*SL, C.BLANCE_NO_NODE)
+	for p, name := range partNames {
+		for i, s := range states {
+			for j, n := range begMap[name].NodesByState[s] {
+				begRows[p*SL+int(off[i])+j] = nodes.get(n)
+			}
+			if e := endMap[name]; e != nil {
+				for j, n := range e.NodesByState[s] {
+					endRows[p*SL+int(off[i])+j] = nodes.get(n)
+				}
+			}
+		}
+	}
+	fav := C.int32_t(0)
+	if favorMinNodes {
+		fav = 1
+	}
+	m := &movesB200{partNames: partNames, nodeNames: nodes.names, nNodeIDs: len(nodes.names)}
+	var total C.int64_t
+	if st := C.blance_moves_create(b200(), C.int32_t(P), C.int32_t(S), C.int32_t(S), pOff, pBeg, pEnd, fav,
+		C.int32_t(m.nNodeIDs), &m.h, &total); st != C.BLANCE_OK {
+		return nil, nil // the caller keeps the Go loop of orchestrate.go:273-287
+	}
+	opOff := make([]C.int64_t, P+1)
+	opNode := make([]C.int32_t, int(total)+1)
+	opState := make([]C.uint8_t, int(total)+1)
+	opKind := make([]C.uint8_t, int(total)+1)
+	if st := C.blance_moves_fetch(b200(), m.h, &opOff[0], &opNode[0], &opState[0], &opKind[0]); st != C.BLANCE_OK {
+		C.blance_moves_free(b200(), m.h)
+		return nil, nil
+	}
+	kinds := [...]string{"add", "del", "promote", "demote"}
+	out := make(map[string]*NextMoves, P)
+	for p, name := range partNames {
+		moves := make([]NodeStateOp, 0, int(opOff[p+1]-opOff[p]))
+		for k := opOff[p]; k < opOff[p+1]; k++ {
+			st := ""
+			if opState[k] != C.BLANCE_OP_STATE_NONE {
+				st = states[opState[k]]
+			}
+			moves = append(moves, NodeStateOp{Node: m.nodeNames[opNode[k]], State: st, Op: kinds[opKind[k]]})
+		}
+		out[name] = &NextMoves{Partition: name, Next: 0, Moves: moves}
+	}
+	return out, m
+}
+
+// availableMovesB200 answers one round of findAvailableMovesUnlocked (orchestrate.go:749-763): for the cursors
+// of `next` (partition name -> NextMoves.Next) it returns, per node, the partitions whose next move is on that
+// node, and the partition LowestWeightPartitionMoveForNode (orchestrate.go:177-186) would pick there.
+func (m *movesB200) availableMovesB200(next map[string]int) (byNode map[string][]string, best map[string]string) {
+	P := len(m.partNames)
+	cur := make([]C.int32_t, P+1)
+	for p, name := range m.partNames {
+		cur[p] = C.int32_t(next[name])
+	}
+	nodeOff := make([]C.int32_t, m.nNodeIDs+1)
+	nodeParts := make([]C.int32_t, P+1)
+	bestPart := make([]C.int32_t, m.nNodeIDs+1)
+	if st := C.blance_moves_available(b200(), m.h, &cur[0], &nodeOff[0], &nodeParts[0], &bestPart[0]); st != C.BLANCE_OK {
+		return nil, nil
+	}
+	byNode, best = map[string][]string{}, map[string]string{}
+	for n := 0; n < m.nNodeIDs; n++ {
+		for k := nodeOff[n]; k < nodeOff[n+1]; k++ {
+			byNode[m.nodeNames[n]] = append(byNode[m.nodeNames[n]], m.partNames[nodeParts[k]])
+		}
+		if bestPart[n] >= 0 {
+			best[m.nodeNames[n]] = m.partNames[bestPart[n]]
+		}
+	}
+	return byNode, best
+}
+
+func (m *movesB200) free() { C.blance_moves_free(b200(), m.h) }
