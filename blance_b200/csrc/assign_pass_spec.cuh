@@ -46,19 +46,21 @@ namespace blance_dev {
 #define SP_LPL 2             // list entries per leader lane
 #define SP_D 2               // ring chunks per scout warp
 #define SP_NPTS 8            // nodes per scout thread in team operations (N <= 32 * SW * SP_NPTS)
+#define SP_GEN_MOD 1023      // ring generations cycle 0..1022; 1023 = never written
+#define SP_LMIN 10           // rebuild the list when fewer entries are left (and it is not complete)
 
 enum : int { SPB_ALL = 8, SPB_GO = 9, SPB_DONE = 10, SPB_TEAM = 11 };
-enum : int32_t { SP_OP_EXIT = 1, SP_OP_FULL = 3 };
+enum : int32_t { SP_OP_EXIT = 1, SP_OP_REBUILD = 2, SP_OP_FULL = 3 };
 enum : uint32_t { SPZ_NEVER = 0x80000000u };
 
 struct SpecCtl {
   uint4 xchg[2][32];                 // team arg-min partials
-  uint4 pubq[64];                    // leader -> publisher: {A offset or -1, delta, epoch, 1 = last entry of its epoch}
+  uint4 cand[64];                    // rebuild: extracted {key hi, key lo, node, -}
+  uint4 bound[32];                   // rebuild: per-warp lower bound of what was not extracted
+  uint4 ins[16];                     // list inserts of a mover
   alignas(16) int32_t slot_bit[BL_SLP_MAX];
   alignas(8) unsigned long long mbar[32 * SP_D];
   int32_t epoch, front, cmd_seq, cmd_op, cmd_arg, cmd_epoch;
-  int32_t pub_head, pub_done, pub_quit, commit_done;
-  int32_t abort_flag;                // a wait loop gave up (never in a correct run): every role leaves, the host reports an error
   int32_t res_n, res_same;
   int32_t res_chosen[BL_K_MAX];
 };
@@ -66,8 +68,8 @@ struct SpecCtl {
 __host__ __device__ inline size_t spec_dyn_smem_bytes(int N, int SW) {
   const size_t H = (size_t)32 * SW * SP_D;
   const size_t Np = ((size_t)N + 3) & ~(size_t)3;        // every array starts 16-byte aligned
-  size_t b = Np * 32 + Np * 8 + Np * 4 + Np * 4 + ((Np + 15) & ~(size_t)15);   // mirror, base keys, totals, stamps, flags
-  b += H * 64 + H * 16 + H * 16 + H;   // records (<= 16 words), qstat, results, accepted ranks
+  size_t b = Np * 32 + Np * 4 + Np * 4 + ((Np + 15) & ~(size_t)15);
+  b += H * 64 + H * 16 + H * 16;       // records (<= 16 words), qstat, results
   return b;
 }
 
@@ -117,53 +119,24 @@ __device__ __forceinline__ unsigned long long sp_key(double cd, double ff, doubl
   return score_key(r);
 }
 
-// warp arg-min of (hi, lo, pos): one redux when the high words already decide it
-__device__ __forceinline__ Best warp_argmin_q(Best v) {
-  const unsigned full = 0xFFFFFFFFu;
-  const uint32_t mhi = __reduce_min_sync(full, v.hi);
-  const uint32_t eq = __ballot_sync(full, v.hi == mhi);
-  if ((eq & (eq - 1u)) == 0u) {
-    const int src = __ffs(eq) - 1;
-    return Best{mhi, __shfl_sync(full, v.lo, src), __shfl_sync(full, v.pos, src)};
-  }
-  const uint32_t lo2 = (v.hi == mhi) ? v.lo : 0xFFFFFFFFu;
-  const uint32_t mlo = __reduce_min_sync(full, lo2);
-  const uint32_t p2 = (lo2 == mlo && v.hi == mhi) ? v.pos : 0xFFFFFFFFu;
-  return Best{mhi, mlo, __reduce_min_sync(full, p2)};
-}
-
-// base key: the score with nodeToNodeCounts = 0 and no stickiness (cd + 0/P == cd exactly)
-__device__ __forceinline__ unsigned long long sp_base_key(double cd, double ff, double wd, double wy, bool boost, bool has_nw) {
-  const double base = __dadd_rn(cd, ff);
-  double r = base;
-  if (has_nw && !boost) r = div_exact(r, wd, wy);
-  if (boost) { double b = -wd; if (b < 0.0) b = 0.0; r = __dadd_rn(base, b); }
-  return score_key(r);
-}
-
 __device__ __forceinline__ bool lex_lt(unsigned long long ka, uint32_t pa, unsigned long long kb, uint32_t pb) {
   return ka < kb || (ka == kb && pa < pb);
 }
 
 // K = the state's constraints (1..BL_FAST_K).  blockDim.x = 32 * NW warps; warp 0 is the leader, the warps
-// of idle_mask exit at once (they keep the leader's scheduler free), the first of the others is the PUBLISHER
-// (it applies the movers' updates of A and publishes the epochs, so that the leader never waits for a fence
-// over global atomics), the rest are the SW scouts.  SW * SP_D must be a power of two (swd_shift = its log2).
+// of idle_mask exit at once (they keep the leader's scheduler free), the others are the SW scouts.
 template <int K>
-__global__ void __launch_bounds__(448, 1) k_assign_pass_spec(DPool pool, int s, int SW, unsigned idle_mask, int swd_shift) {
+__global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, int SW, unsigned idle_mask, int /*unused*/) {
   DInst& D = pool.insts[blockIdx.x];
   if (!D.active || s >= D.S || D.pass_mode != 2) return;
   if (D.state_constraints[s] != K) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if ((idle_mask >> warp) & 1u) return;
   const bool is_leader = warp == 0;
-  const int arank = __popc(~idle_mask & ((1u << warp) - 1u));           // rank among the active warps: 0 leader, 1 publisher, 2 committer
-  const bool is_pub = arank == 1, is_com = arank == 2;
-  const int sidx = arank - 3;                                           // scout number
-  const int NTA = 32 * (SW + 3), TS = 32 * SW, NTT = 32 * (SW + 1);     // all active threads / scouts / scouts + leader
-  const int atid = arank * 32 + lane;                                   // rank among the active threads
+  const int sidx = __popc(~idle_mask & ((1u << warp) - 1u)) - 1;        // scout number (leader: -1)
+  const int NTA = 32 * (SW + 1), TS = 32 * SW;
+  const int atid = is_leader ? lane : 32 + sidx * 32 + lane;             // rank among the active threads
   const int SWD = SW * SP_D, H = 32 * SWD;
-  const uint32_t swd_mask = (uint32_t)SWD - 1u;
 
   __shared__ SpecCtl ctl;
   extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -194,14 +167,12 @@ __global__ void __launch_bounds__(448, 1) k_assign_pass_spec(DPool pool, int s, 
   const uint32_t base_a = (uint32_t)__cvta_generic_to_shared(dyn_smem);
   const uint32_t Np = ((uint32_t)N + 3u) & ~3u;                  // (padded: every array starts 16-byte aligned)
   const uint32_t nd_a = base_a;                                  // mirror: {cd, ff, wd, wy} per node
-  const uint32_t bk_a = nd_a + 32u * Np;                         // base key of every node (score with n2n = 0, no stickiness)
-  const uint32_t tot_a = bk_a + 8u * Np;                         // all-state totals
+  const uint32_t tot_a = nd_a + 32u * Np;                        // all-state totals
   const uint32_t chg_a = tot_a + 4u * Np;                        // lastchg
   const uint32_t flg_a = chg_a + 4u * Np;                        // NF_VALID | NF_BOOST
   const uint32_t rec_a = flg_a + ((Np + 15u) & ~15u);            // ring: records
   const uint32_t qs_a = rec_a + (uint32_t)H * RECB;              // ring: qstat (4 per step)
   const uint32_t dyn_a = qs_a + (uint32_t)H * 16u;               // ring: scout results
-  const uint32_t acc_a = dyn_a + (uint32_t)H * 16u;              // ring: what the leader decided (0x80 | ranks: sticky; 1: resolved)
   const uint32_t ctl_a = (uint32_t)__cvta_generic_to_shared(&ctl);
   const uint32_t xchg_a = ctl_a + (uint32_t)offsetof(SpecCtl, xchg);
   const uint32_t sbit_a = ctl_a + (uint32_t)offsetof(SpecCtl, slot_bit);
@@ -209,12 +180,6 @@ __global__ void __launch_bounds__(448, 1) k_assign_pass_spec(DPool pool, int s, 
   const uint32_t epoch_a = ctl_a + (uint32_t)offsetof(SpecCtl, epoch);
   const uint32_t front_a = ctl_a + (uint32_t)offsetof(SpecCtl, front);
   const uint32_t seq_a = ctl_a + (uint32_t)offsetof(SpecCtl, cmd_seq);
-  const uint32_t pubq_a = ctl_a + (uint32_t)offsetof(SpecCtl, pubq);
-  const uint32_t pubh_a = ctl_a + (uint32_t)offsetof(SpecCtl, pub_head);
-  const uint32_t pubd_a = ctl_a + (uint32_t)offsetof(SpecCtl, pub_done);
-  const uint32_t pubx_a = ctl_a + (uint32_t)offsetof(SpecCtl, pub_quit);
-  const uint32_t cdone_a = ctl_a + (uint32_t)offsetof(SpecCtl, commit_done);
-  const uint32_t abort_a = ctl_a + (uint32_t)offsetof(SpecCtl, abort_flag);
 
   // ---- pass constants, mirror, ring ------------------------------------------------------------------
   for (int i = atid; i < SLP; i += NTA) {
@@ -236,30 +201,25 @@ __global__ void __launch_bounds__(448, 1) k_assign_pass_spec(DPool pool, int s, 
     const double ff = have_p ? div_exact(__dmul_rn(0.001, (double)t), Pd, Py) : 0.0;   // plan.go:650
     double* nd = reinterpret_cast<double*>(dyn_smem) + 4 * (size_t)n;
     nd[0] = cd; nd[1] = ff; nd[2] = wd; nd[3] = wy;
-    *reinterpret_cast<unsigned long long*>(dyn_smem + (bk_a - base_a) + 8u * n) = sp_base_key(cd, ff, wd, wy, (fl & NF_BOOST) != 0, has_nw);
     sts32(tot_a + 4u * n, t);
     sts32(chg_a + 4u * n, 0);
     dyn_smem[(flg_a - base_a) + n] = (unsigned char)fl;
   }
-  for (int i = atid; i < H; i += NTA) sts128(dyn_a + 16u * i, 0u, 0u, 0x3FFu << 21, 0u);      // generation 1023: never written
+  for (int i = atid; i < H; i += NTA) sts128(dyn_a + 16u * i, 0u, 0u, (uint32_t)SP_GEN_MOD << 21, 0u);
   if (atid == 0) {
     for (int i = 0; i < SWD; ++i) mbar_init(mbar_a + 8u * i, 1);
     ctl.epoch = 0; ctl.front = 0; ctl.cmd_seq = 0; ctl.cmd_op = 0; ctl.cmd_arg = 0; ctl.cmd_epoch = 0;
-    ctl.pub_head = 0; ctl.pub_done = 0; ctl.pub_quit = 0; ctl.commit_done = 0; ctl.abort_flag = 0;
     ctl.res_n = 0; ctl.res_same = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   bar_sync(SPB_ALL, NTA);
 
-  uint32_t slot_blocked = 0;                 // bit sl: slot sl belongs to a higher-priority state (its node is not a candidate)
+  uint32_t slot_blocked = 0;                 // bit sl: a listed node found in slot sl of the row is not a candidate
   uint32_t slot_state_s = 0;                 //         slot sl belongs to the state being assigned
-  uint32_t sbit8[8];                         // state bit of slot sl
-#pragma unroll
-  for (int sl = 0; sl < 8; ++sl) sbit8[sl] = sl < SL ? (uint32_t)lds32(sbit_a + 4u * sl) : 0u;
   for (int sl = 0; sl < SL && sl < 8; ++sl) {
     const uint32_t b = (uint32_t)lds32(sbit_a + 4u * sl);
-    if (b & higher_states) slot_blocked |= 1u << sl;
+    if (b & (higher_states | (1u << s))) slot_blocked |= 1u << sl;
     if (b & (1u << s)) slot_state_s |= 1u << sl;
   }
 
@@ -276,74 +236,8 @@ __global__ void __launch_bounds__(448, 1) k_assign_pass_spec(DPool pool, int s, 
     xbuf ^= 1;
     return warp_argmin(Best{(uint32_t)e.x, (uint32_t)e.y, (uint32_t)e.z});
   };
+  const int M_ext = (64 / SW) < 7 ? (64 / SW) : 7;       // rebuild: entries extracted per scout warp
 
-  if (is_pub) {
-    // =================================== publisher =====================================================
-    // Applies the queued A updates (fire-and-forget atomics), fences them, then publishes the epoch of the last
-    // complete group: a scout that reads epoch e afterwards also sees every update that belongs to epochs <= e.
-    int tail = 0;
-    for (;;) {
-      const int head = lds32v(pubh_a);
-      if (head == tail) {
-        if (lds32v(pubx_a)) break;
-        __nanosleep(40);
-        continue;
-      }
-      const int cnt = (head - tail) < 32 ? (head - tail) : 32;
-      int32_t ep = -1;
-      if (lane < cnt) {
-        const int4 q = lds128(pubq_a + 16u * (uint32_t)((tail + lane) & 63));
-        if (q.x >= 0) atomicAdd(&A[q.x], q.y);
-        if (q.w) ep = q.z;
-      }
-      __threadfence_block();
-      ep = __reduce_max_sync(0xFFFFFFFFu, ep);
-      tail += cnt;
-      if (lane == 0) {
-        if (ep >= 0) sts32v(epoch_a, ep);
-        sts32v(pubd_a, tail);
-      }
-      __syncwarp();
-    }
-    return;
-  }
-  if (is_com) {
-    // =================================== committer =====================================================
-    // Trails the leader: for every step the leader accepted as sticky it bumps nodeToNodeCounts (plan.go:238-245)
-    // and stores the outcome (the ranks of the current nodes); the leader waits for commit_done before it reads
-    // nodeToNodeCounts in a resolve.  Keeps the scattered global atomics out of the leader's instruction stream.
-    uint8_t* srank = pool.srank + D.part_off;
-    int c = 0;
-    for (;;) {
-      const int f = lds32v(front_a);
-      if (f == c) {
-        if (lds32v(pubx_a)) break;
-        __nanosleep(20);
-        continue;
-      }
-      while (c < f) {
-        const int j = c + lane;
-        if (j < f) {
-          const uint32_t cj = (uint32_t)j >> 5;
-          const uint32_t slot = ((cj & swd_mask) << 5) | ((uint32_t)j & 31u);
-          const uint32_t a = dyn_smem[(acc_a - base_a) + slot];
-          if (a & 0x80u) {
-            const uint32_t reca = rec_a + slot * RECB;
-            if (have_p) {
-              const int32_t top = lds32(reca + (uint32_t)(SLP + 2) * 4u);
-#pragma unroll
-              for (int q = 0; q < K; ++q) atomicAdd(&G[(size_t)top * N + lds32(reca + (uint32_t)(lo_s + q) * 4u)], 1);
-            }
-            srank[j] = (uint8_t)a;
-          }
-        }
-        c = (c + 32 < f) ? c + 32 : f;
-      }
-      __syncwarp();
-      if (lane == 0) sts32v(cdone_a, c);
-    }
-    return;
-  }
   if (!is_leader) {
     // =================================== scouts ========================================================
     int chunk[SP_D];
@@ -378,16 +272,16 @@ __global__ void __launch_bounds__(448, 1) k_assign_pass_spec(DPool pool, int s, 
         const int seq = lds32v(seq_a);
         if (seq != my_seq) {
           my_seq = seq;
-          bar_sync(SPB_GO, NTT);
+          bar_sync(SPB_GO, NTA);
           const int op = *(volatile int32_t*)&ctl.cmd_op;
           if (op == SP_OP_EXIT) goto scouts_done;
-          bool changed = false;
+          bool changed = true;
           const int32_t E1 = *(volatile int32_t*)&ctl.cmd_epoch;
           if (op == SP_OP_FULL) {
             // ---- full evaluation of step cmd_arg (the lock-step kernel's step) from the mirror --------------
             const int i = *(volatile int32_t*)&ctl.cmd_arg;
             const int ci = i >> 5;
-            const uint32_t slot = (((uint32_t)ci & swd_mask) << 5) | (uint32_t)(i & 31);
+            const uint32_t slot = (uint32_t)(ci % SWD) * 32u + (uint32_t)(i & 31);
             const uint32_t reca = rec_a + slot * RECB;
             const int4 hdr = lds128(reca + (uint32_t)SLP * 4u);               // meta, w_p, top, partition
             const int32_t w_p = hdr.y, top = hdr.z;
@@ -469,21 +363,52 @@ __global__ void __launch_bounds__(448, 1) k_assign_pass_spec(DPool pool, int s, 
                     if (have_p) nd[1] = div_exact(__dmul_rn(0.001, (double)t), Pd, Py);
                   }
                   sts32(chg_a + 4u * n, E1);
-                  *reinterpret_cast<unsigned long long*>(dyn_smem + (bk_a - base_a) + 8u * n) =
-                      sp_base_key(cd, nd[1], nd[2], nd[3], (dyn_smem[(flg_a - base_a) + n] & NF_BOOST) != 0, has_nw);
                 }
               }
             }
+            if (changed) bar_sync(SPB_TEAM, TS);          // the mirror is final before the base keys are read
           }
-          if (changed) __threadfence_block();         // my atomics on A are ordered before the epoch the leader queues
-          bar_sync(SPB_DONE, NTT);
+          if (changed) {
+            // ---- rebuild: every scout warp extracts its M_ext smallest base keys and a lower bound of the rest ---
+            unsigned long long bkey[SP_NPTS];
+            uint32_t live = 0;
+#pragma unroll
+            for (int j = 0; j < SP_NPTS; ++j) {
+              const int n = team_node(j);
+              bkey[j] = ~0ull;
+              if (n < N && (dyn_smem[(flg_a - base_a) + n] & NF_VALID)) {
+                const int4 ma = lds128(nd_a + (uint32_t)n * 32u), mb = lds128(nd_a + (uint32_t)n * 32u + 16u);
+                const uint32_t fl = dyn_smem[(flg_a - base_a) + n];
+                bkey[j] = sp_key(__hiloint2double(ma.y, ma.x), __hiloint2double(ma.w, ma.z), __hiloint2double(mb.y, mb.x),
+                                 __hiloint2double(mb.w, mb.z), (fl & NF_BOOST) != 0, has_nw, 0, 0.0, have_p, Pd, Py);
+                live |= 1u << j;
+              }
+            }
+            for (int r = 0; r <= M_ext; ++r) {
+              unsigned long long bk = ~0ull;
+              uint32_t bpos = 0xFFFFFFFFu;
+#pragma unroll
+              for (int j = 0; j < SP_NPTS; ++j)
+                if (((live >> j) & 1u) && (bpos == 0xFFFFFFFFu || bkey[j] < bk)) { bk = bkey[j]; bpos = (uint32_t)team_node(j); }
+              const Best b = warp_argmin(Best{(uint32_t)(bk >> 32), (uint32_t)bk, bpos});
+              if (r < M_ext) {
+                if (lane == 0) ctl.cand[sidx * M_ext + r] = make_uint4(b.hi, b.lo, b.pos, 0u);
+#pragma unroll
+                for (int j = 0; j < SP_NPTS; ++j)
+                  if ((uint32_t)team_node(j) == b.pos) live &= ~(1u << j);
+              } else if (lane == 0) {
+                ctl.bound[sidx] = make_uint4(b.hi, b.lo, b.pos, 0u);      // all-ones when nothing is left
+              }
+            }
+          }
+          bar_sync(SPB_DONE, NTA);
         }
         // ---- my chunk of ring slot d -------------------------------------------------------------------
         int c = chunk[d];
         if (c * 32 >= n_assign) continue;
         any_work = true;
-        const int fr = lds32v(cdone_a);
-        if (fr >= (c + 1) * 32) {                       // consumed (by the leader AND the committer): the slot takes its next chunk
+        const int fr = lds32v(front_a);
+        if (fr >= (c + 1) * 32) {                       // consumed: the slot takes its next chunk
           c += SWD;
           chunk[d] = c;
           loaded[d] = false;
@@ -503,7 +428,7 @@ __global__ void __launch_bounds__(448, 1) k_assign_pass_spec(DPool pool, int s, 
         if (e0 == seen_epoch[d]) continue;
         const uint32_t slot = (uint32_t)(sidx + SW * d) * 32u + (uint32_t)lane;
         const int j = c * 32 + lane;
-        const uint32_t gen = ((uint32_t)c >> swd_shift) & 0x3FFu;
+        const uint32_t gen = (uint32_t)((c / SWD) % SP_GEN_MOD);
         const uint32_t reca = rec_a + slot * RECB;
         const bool live = j < n_assign;
         const int n_cur = lds32(reca + (uint32_t)(SLP + 6) * 4u);
@@ -569,7 +494,7 @@ __global__ void __launch_bounds__(448, 1) k_assign_pass_spec(DPool pool, int s, 
     }
   scouts_done:
     // ---- write the per-node counts of this state back ------------------------------------------------------
-    for (int n = sidx * 32 + lane; n < N; n += TS) counts[s * N + n] = __double2int_rn(reinterpret_cast<double*>(dyn_smem)[4 * (size_t)n]);
+    for (int n = atid - 32; n < N; n += TS) counts[s * N + n] = __double2int_rn(reinterpret_cast<double*>(dyn_smem)[4 * (size_t)n]);
     return;
   }
 
@@ -578,15 +503,12 @@ __global__ void __launch_bounds__(448, 1) k_assign_pass_spec(DPool pool, int s, 
   int32_t Ln[SP_LPL];
 #pragma unroll
   for (int u = 0; u < SP_LPL; ++u) { Lk[u] = ~0ull; Ln[u] = -1; }
-  unsigned long long ubk = ~0ull, B0k = ~0ull, lb1k = ~0ull;      // lb1: lower bound of the second-column entries
-  uint32_t ubp = 0xFFFFFFFFu, B0p = 0xFFFFFFFFu, lb1p = 0xFFFFFFFFu;
-  long long n_round2 = 0;
+  unsigned long long ubk = ~0ull, B0k = ~0ull;
+  uint32_t ubp = 0xFFFFFFFFu, B0p = 0xFFFFFFFFu;
   int32_t E = 0;
-  int seq = 0, pub_head = 0, movers_since_rebuild = 0;
-  bool b0_clamped = false;
-  long long n_fast = 0, n_res = 0, n_mov = 0, n_team = 0, n_reb = 0, n_wait = 0, n_stale = 0, n_cwait = 0;
-  long long why[4] = {0, 0, 0, 0};
-  long long cyc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc = clock64();
+  int seq = 0;
+  long long n_fast = 0, n_res = 0, n_mov = 0, n_team = 0, n_reb = 0, n_wait = 0, n_stale = 0;
+  long long cyc[6] = {0, 0, 0, 0, 0, 0}, tc = clock64();
   const long long t_begin = tc;
 #ifdef BLANCE_SPEC_TIMING
 #define SP_T(ix) do { const long long n_ = clock64(); cyc[ix] += n_ - tc; tc = n_; } while (0)
@@ -594,21 +516,6 @@ __global__ void __launch_bounds__(448, 1) k_assign_pass_spec(DPool pool, int s, 
 #define SP_T(ix) do { } while (0)
 #endif
 
-  // Watchdog of the leader's wait loops: a correct run never gets near the limit; if one does, say where and stop
-  // the pass (the plan then fails with BLANCE_ERR_CUDA instead of hanging the GPU).
-  long long spins = 0;
-  auto stuck = [&](int where, int a, int b) {
-    if (++spins < (1ll << 26)) return false;
-    if (lane == 0) {
-      printf("[blance] speculative pass stuck (wait %d) at step %d of %d: %d %d | front %d commit_done %d epoch %d pub %d/%d\n", where, a, n_assign, b, 0,
-             *(volatile int32_t*)&ctl.front, *(volatile int32_t*)&ctl.commit_done, *(volatile int32_t*)&ctl.epoch,
-             *(volatile int32_t*)&ctl.pub_done, *(volatile int32_t*)&ctl.pub_head);
-      sts32v(abort_a, 1);
-      D.spec_abort = 1;
-    }
-    return true;
-  };
-  bool aborted = false;
   auto team_cmd = [&](int op, int arg) {
     if (lane == 0) {
       *(volatile int32_t*)&ctl.cmd_op = op;
@@ -618,19 +525,8 @@ __global__ void __launch_bounds__(448, 1) k_assign_pass_spec(DPool pool, int s, 
       sts32v(seq_a, ++seq);
     } else ++seq;
     __syncwarp();
-    bar_sync(SPB_GO, NTT);
-    if (op != SP_OP_EXIT) bar_sync(SPB_DONE, NTT);
-  };
-  // The list.  Lane l owns the nodes n = l (mod 32): its two entries are (after a rebuild) the two smallest base
-  // keys of its class and (ublk, ublp) bounds every unlisted node of the class from below; ub = the smallest of
-  // the 32 lane bounds.  Updates stay inside the owner lane; a rebuild is a scan of the base keys in shared
-  // memory by the leader alone.  B0 = min(smallest listed key, ub) is a lower bound of every live base key.
-  unsigned long long ublk = ~0ull;
-  uint32_t ublp = 0xFFFFFFFFu;
-  auto recompute_ub = [&]() {
-    const Best b = warp_argmin_q(Best{(uint32_t)(ublk >> 32), (uint32_t)ublk, ublp});
-    ubk = ((unsigned long long)b.hi << 32) | b.lo;
-    ubp = b.pos;
+    bar_sync(SPB_GO, NTA);
+    if (op != SP_OP_EXIT) bar_sync(SPB_DONE, NTA);
   };
   auto recompute_b0 = [&]() {
     unsigned long long bk = ~0ull;
@@ -638,308 +534,171 @@ __global__ void __launch_bounds__(448, 1) k_assign_pass_spec(DPool pool, int s, 
 #pragma unroll
     for (int u = 0; u < SP_LPL; ++u)
       if (Ln[u] >= 0 && lex_lt(Lk[u], (uint32_t)Ln[u], bk, bp)) { bk = Lk[u]; bp = (uint32_t)Ln[u]; }
-    const Best b = warp_argmin_q(Best{(uint32_t)(bk >> 32), (uint32_t)bk, bp});
-    B0k = ((unsigned long long)b.hi << 32) | b.lo;
-    B0p = b.pos;
-    b0_clamped = !lex_lt(B0k, B0p, ubk, ubp);
-    if (b0_clamped) { B0k = ubk; B0p = ubp; }
+    const Best b = warp_argmin(Best{(uint32_t)(bk >> 32), (uint32_t)bk, bp});
+    if (b.pos != 0xFFFFFFFFu) { B0k = ((unsigned long long)b.hi << 32) | b.lo; B0p = b.pos; }
+    else { B0k = ubk; B0p = ubp; }
   };
-  auto rebuild_list = [&]() {               // the two smallest base keys of my class, and the third as my bound
-    unsigned long long k0 = ~0ull, k1 = ~0ull, k2 = ~0ull;
-    uint32_t n0 = 0xFFFFFFFFu, n1 = 0xFFFFFFFFu, n2 = 0xFFFFFFFFu;
-    for (int n = lane; n < N; n += 32) {
-      if (!(dyn_smem[(flg_a - base_a) + n] & NF_VALID)) continue;
-      const unsigned long long k = *reinterpret_cast<const volatile unsigned long long*>(dyn_smem + (bk_a - base_a) + 8u * n);
-      if (lex_lt(k, (uint32_t)n, k2, n2)) {
-        if (lex_lt(k, (uint32_t)n, k1, n1)) {
-          k2 = k1; n2 = n1;
-          if (lex_lt(k, (uint32_t)n, k0, n0)) { k1 = k0; n1 = n0; k0 = k; n0 = (uint32_t)n; }
-          else { k1 = k; n1 = (uint32_t)n; }
-        } else { k2 = k; n2 = (uint32_t)n; }
+  auto adopt_list = [&]() {                 // after a team rebuild: cand[] / bound[] -> list, ub, B0
+    uint4 bb = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);
+    if (lane < SW) bb = ctl.bound[lane];
+    const Best ub = warp_argmin(Best{bb.x, bb.y, bb.z});
+    ubk = ((unsigned long long)ub.hi << 32) | ub.lo;
+    ubp = ub.pos;
+    const int n_cand = SW * M_ext;
+#pragma unroll
+    for (int u = 0; u < SP_LPL; ++u) {
+      Lk[u] = ~0ull; Ln[u] = -1;
+      const int x = lane + 32 * u;
+      if (x < n_cand) {
+        const uint4 c = ctl.cand[x];
+        const unsigned long long k = ((unsigned long long)c.x << 32) | c.y;
+        if (c.z != 0xFFFFFFFFu && lex_lt(k, c.z, ubk, ubp)) { Lk[u] = k; Ln[u] = (int32_t)c.z; }
       }
-    }
-    Lk[0] = k0; Ln[0] = (int32_t)n0; Lk[1] = k1; Ln[1] = (int32_t)n1;      // (n = 0xFFFFFFFF reads as -1: no entry)
-    ublk = k2; ublp = n2;
-    recompute_ub();
-    {
-      const Best b = warp_argmin_q(Best{(uint32_t)(k1 >> 32), (uint32_t)k1, n1});
-      lb1k = ((unsigned long long)b.hi << 32) | b.lo;
-      lb1p = b.pos;
     }
     recompute_b0();
-    movers_since_rebuild = 0;
     ++n_reb;
   };
-  // a node whose base key changed: its owner lane updates / lists / bounds it.  tk is its new key (tvalid: live)
-  auto list_touch = [&](int32_t tx, unsigned long long tk, bool tvalid) {
-    bool ub_moved = false;
-    if ((tx & 31) == lane) {
-      if (Ln[0] == tx) { if (tvalid) Lk[0] = tk; else { Ln[0] = -1; Lk[0] = ~0ull; } }
-      else if (Ln[1] == tx) { if (tvalid) Lk[1] = tk; else { Ln[1] = -1; Lk[1] = ~0ull; } }
-      else if (tvalid && lex_lt(tk, (uint32_t)tx, ublk, ublp)) {          // below my bound: it has to be listed
-        if (Ln[0] < 0) { Ln[0] = tx; Lk[0] = tk; }
-        else if (Ln[1] < 0) { Ln[1] = tx; Lk[1] = tk; }
-        else {
-          const int big = lex_lt(Lk[0], (uint32_t)Ln[0], Lk[1], (uint32_t)Ln[1]) ? 1 : 0;
-          unsigned long long ek = tk;
-          uint32_t en = (uint32_t)tx;                                     // the one that stays out: the largest of the three
-          if (lex_lt(tk, (uint32_t)tx, Lk[big], (uint32_t)Ln[big])) { ek = Lk[big]; en = (uint32_t)Ln[big]; Lk[big] = tk; Ln[big] = tx; }
-          if (lex_lt(ek, en, ublk, ublp)) { ublk = ek; ublp = en; ub_moved = true; }
-        }
-      }
-      if (Ln[0] >= 0 && Ln[1] >= 0 && lex_lt(Lk[1], (uint32_t)Ln[1], Lk[0], (uint32_t)Ln[0])) {   // smaller entry first
-        const unsigned long long k = Lk[0]; Lk[0] = Lk[1]; Lk[1] = k;
-        const int32_t n = Ln[0]; Ln[0] = Ln[1]; Ln[1] = n;
-      } else if (Ln[0] < 0 && Ln[1] >= 0) { Lk[0] = Lk[1]; Ln[0] = Ln[1]; Lk[1] = ~0ull; Ln[1] = -1; }
-    }
-    // lb1 bounds the second-column entries from below: it moves when the node sits there now with a smaller key
-    if (__any_sync(0xFFFFFFFFu, (tx & 31) == lane && Ln[1] >= 0 && lex_lt(Lk[1], (uint32_t)Ln[1], lb1k, lb1p))) {
-      const int o = tx & 31;
-      lb1k = __shfl_sync(0xFFFFFFFFu, Lk[1], o);
-      lb1p = (uint32_t)__shfl_sync(0xFFFFFFFFu, Ln[1], o);
-    }
-    if (__any_sync(0xFFFFFFFFu, ub_moved)) recompute_ub();
-  };
-  // Hands epoch E + 1 to the publisher: the A updates of the lanes with `has`, then the marker that lets it
-  // publish.  The mirror / lastchg stores above are ordinary shared-memory stores of this warp, issued before
-  // the store of pub_head, so whoever sees the epoch also sees them.
-  auto publish = [&](bool has, int32_t idx, int32_t dA) {
-    const uint32_t m = __ballot_sync(0xFFFFFFFFu, has);
-    const int n = __popc(m) + 1;
-    while (pub_head + n - lds32v(pubd_a) > 64) { __nanosleep(20); if (stuck(1, pub_head, n)) { aborted = true; break; } }
-    if (has) sts128(pubq_a + 16u * (uint32_t)((pub_head + __popc(m & ((1u << lane) - 1u))) & 63), (uint32_t)idx, (uint32_t)dA, (uint32_t)(E + 1), 0u);
-    if (lane == 0) sts128(pubq_a + 16u * (uint32_t)((pub_head + n - 1) & 63), 0xFFFFFFFFu, 0u, (uint32_t)(E + 1), 1u);
-    pub_head += n;
+  auto publish_epoch = [&]() {
+    __threadfence_block();
     __syncwarp();
-    if (lane == 0) sts32v(pubh_a, pub_head);
     ++E;
+    if (lane == 0) sts32v(epoch_a, E);
   };
 
-  rebuild_list();
-  SP_T(6);
+  team_cmd(SP_OP_REBUILD, 0);
+  adopt_list();
+  SP_T(4);
 
   int i = 0;
-  // The leader looks at the steps in aligned windows of 64 (two per lane).  A window is loaded once - results,
-  // current nodes, and the stamp test of every result - and stays in registers: after a mover the rest of the
-  // window is judged again from the registers (a result whose current node the mover touched is dropped, the
-  // others only meet the new B0), so a mover costs a ballot, not a reload.
-  int w = -64;                                   // base of the window in registers
-  int4 r[2];
-  int32_t cn[2][K];
-  uint32_t slotv[2];
-  bool have[2], never[2], fresh[2];
-#pragma unroll
-  for (int u = 0; u < 2; ++u) { r[u] = make_int4(0, 0, 0, 0); slotv[u] = 0; have[u] = never[u] = fresh[u] = false; for (int q = 0; q < K; ++q) cn[u][q] = 0; }
   while (i < n_assign) {
-    if (i >= w + 64) {
-      w = i & ~63;
+    // ---- a group of 32 steps: accept the leading run of results that are still exact and sticky ----------------
+    const int j = i + lane;
+    const int cj = j >> 5;
+    const uint32_t slot = (uint32_t)(cj % SWD) * 32u + (uint32_t)(j & 31);
+    const uint32_t gen = (uint32_t)((cj / SWD) % SP_GEN_MOD);
+    const uint32_t reca = rec_a + slot * RECB;
+    const int4 r = lds128(dyn_a + slot * 16u);
+    int32_t cn[K];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int j = w + 32 * u + lane;
-        const uint32_t cj = (uint32_t)j >> 5;
-        const uint32_t slot = ((cj & swd_mask) << 5) | ((uint32_t)j & 31u);
-        slotv[u] = slot;
-        r[u] = lds128(dyn_a + slot * 16u);
+    for (int q = 0; q < K; ++q) cn[q] = lds32(reca + (uint32_t)(lo_s + q) * 4u);
+    const bool live = j < n_assign;
+    const bool have = live && (((uint32_t)r.z >> 21) & 0x3FFu) == gen;
+    const bool never = ((uint32_t)r.z & SPZ_NEVER) != 0;
+    bool fresh = have && !never;
+    if (fresh) {
 #pragma unroll
-        for (int q = 0; q < K; ++q) cn[u][q] = lds32(rec_a + slot * RECB + (uint32_t)(lo_s + q) * 4u);
-        have[u] = j < n_assign && (((uint32_t)r[u].z >> 21) & 0x3FFu) == ((cj >> swd_shift) & 0x3FFu);
-        never[u] = ((uint32_t)r[u].z & SPZ_NEVER) != 0;
-        fresh[u] = have[u] && !never[u];
+      for (int q = 0; q < K; ++q) fresh = fresh && lds32(chg_a + 4u * (uint32_t)cn[q]) <= r.w;
+    }
+    const unsigned long long T = ((unsigned long long)(uint32_t)r.x << 32) | (uint32_t)r.y;
+    const bool ok = fresh && lex_lt(T, (uint32_t)r.z & 0x1FFFu, B0k, B0p);
+    const uint32_t okm = __ballot_sync(0xFFFFFFFFu, ok);
+    const int run = (okm == 0xFFFFFFFFu) ? 32 : (__ffs(~okm) - 1);
+    if (lane < run) {                                                   // commit: plan.go:238-245 and the step's outcome
+      const int32_t top = lds32(reca + (uint32_t)(SLP + 2) * 4u);
+      int32_t* orec = ostream + (size_t)j * REC;
+#pragma unroll
+      for (int q = 0; q < K; ++q) {
+        if (have_p) atomicAdd(&G[(size_t)top * N + cn[q]], 1);
+        orec[((uint32_t)r.z >> (13 + 2 * q)) & 3u] = cn[q];
       }
-#pragma unroll
-      for (int u = 0; u < 2; ++u)
-        if (fresh[u]) {
-#pragma unroll
-          for (int q = 0; q < K; ++q) fresh[u] = fresh[u] && lds32(chg_a + 4u * (uint32_t)cn[u][q]) <= r[u].w;
-        }
+      orec[K] = K;
     }
-    // ---- accept the leading run of results that are exact and sticky ------------------------------------------------
-    const int done = i - w;                        // window positions below `done` are behind the leader
-    bool ok[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const unsigned long long T = ((unsigned long long)(uint32_t)r[u].x << 32) | (uint32_t)r[u].y;
-      ok[u] = (32 * u + lane < done) || (fresh[u] && lex_lt(T, (uint32_t)r[u].z & 0x1FFFu, B0k, B0p));
-    }
-    const uint32_t okm0 = __ballot_sync(0xFFFFFFFFu, ok[0]), okm1 = __ballot_sync(0xFFFFFFFFu, ok[1]);
-    const int f = okm0 != 0xFFFFFFFFu ? (__ffs(~okm0) - 1) : (okm1 != 0xFFFFFFFFu ? 32 + (__ffs(~okm1) - 1) : 64);
-#pragma unroll
-    for (int u = 0; u < 2; ++u)
-      if (32 * u + lane >= done && 32 * u + lane < f)                     // accepted: the committer does the rest
-        dyn_smem[(acc_a - base_a) + slotv[u]] = (unsigned char)(0x80u | (((uint32_t)r[u].z >> 13) & 0xFFu));
-    n_fast += f - done;
-    i = w + f;
-    __syncwarp();
-    if (f > done && lane == 0) sts32v(front_a, i);
-    if (aborted) break;
-    if (f == 64 || i >= n_assign) continue;
+    i += run;
+    n_fast += run;
+    if (run > 0 && lane == 0) sts32v(front_a, i);
     SP_T(0);
+    if (run == 32 || i >= n_assign) continue;
     // ---- step i was not accepted -----------------------------------------------------------------------------------
-    const uint32_t slot_i = ((((uint32_t)i >> 5) & swd_mask) << 5) | ((uint32_t)i & 31u);
-    {
-      const bool fr = f < 32 ? fresh[0] : fresh[1];
-      if (!__shfl_sync(0xFFFFFFFFu, (int)fr, f & 31)) {
-        // no usable result in the registers: its scout may have written one since the window was loaded
-        const int4 rr = lds128(dyn_a + slot_i * 16u);
-        const bool hv = (((uint32_t)rr.z >> 21) & 0x3FFu) == ((((uint32_t)i >> 5) >> swd_shift) & 0x3FFu);
-        if (!hv) {                                                        // its scout has not got there yet
-          ++n_wait; __nanosleep(40); SP_T(1);
-          if (stuck(2, i, (int)rr.z)) { aborted = true; break; }
-          continue;
-        }
-        spins = 0;
-        bool frs = !((uint32_t)rr.z & SPZ_NEVER);
-        if (frs) {
-#pragma unroll
-          for (int q = 0; q < K; ++q) frs = frs && lds32(chg_a + 4u * (uint32_t)lds32(rec_a + slot_i * RECB + (uint32_t)(lo_s + q) * 4u)) <= rr.w;
-        }
-        const unsigned long long T = ((unsigned long long)(uint32_t)rr.x << 32) | (uint32_t)rr.y;
-        if (frs && lex_lt(T, (uint32_t)rr.z & 0x1FFFu, B0k, B0p)) {     // it is sticky after all
-          if (lane == 0) {
-            dyn_smem[(acc_a - base_a) + slot_i] = (unsigned char)(0x80u | (((uint32_t)rr.z >> 13) & 0xFFu));
-            sts32v(front_a, i + 1);
-          }
-          ++i;
-          ++n_fast;
-          w = -128;                                                       // its neighbours may be new as well: reload the window
-          continue;
-        }
-        if (!((uint32_t)rr.z & SPZ_NEVER) && !frs) ++n_stale;
-      }
-    }
+    const bool have_i = __shfl_sync(0xFFFFFFFFu, (int)have, run) != 0;
+    if (!have_i) { ++n_wait; if (run == 0) __nanosleep(100); SP_T(1); continue; }        // its scout has not got there yet
+    if (__shfl_sync(0xFFFFFFFFu, (int)(have && !never && !fresh), run)) ++n_stale;
     ++n_res;
     {
+      const int ci = i >> 5;
+      const uint32_t slot_i = (uint32_t)(ci % SWD) * 32u + (uint32_t)(i & 31);
       const uint32_t rb = rec_a + slot_i * RECB;
-      if (lane == 0) dyn_smem[(acc_a - base_a) + slot_i] = 1;            // the leader writes this step's outcome itself
       const int4 hdr = lds128(rb + (uint32_t)SLP * 4u);               // meta, w_p, top, partition
       const int32_t w_p = hdr.y, top = hdr.z;
       const double stick = lds64f(rb + (uint32_t)SLP * 4u + 16u);
       const int n_cur = lds32(rb + (uint32_t)(SLP + 6) * 4u);
       const bool row_clean = lds32(rb + (uint32_t)(SLP + 7) * 4u) != 0;
-      // the row, in every lane (two broadcast loads); slots beyond SLP read as empty
-      int32_t rowv[8];
-      {
-        const int4 r0 = lds128(rb);
-        const int4 r1 = SLP > 4 ? lds128(rb + 16u) : make_int4(BLANCE_NO_NODE, BLANCE_NO_NODE, BLANCE_NO_NODE, BLANCE_NO_NODE);
-        rowv[0] = r0.x; rowv[1] = r0.y; rowv[2] = r0.z; rowv[3] = r0.w;
-        rowv[4] = r1.x; rowv[5] = r1.y; rowv[6] = r1.z; rowv[7] = r1.w;
-      }
-      const int32_t mycur = lane < n_cur ? lds32(rb + (uint32_t)(lo_s + (lane & 7)) * 4u) : -1;   // lane q: q-th current node
+      const int32_t myslot = lane < SLP ? lds32(rb + 4u * (uint32_t)lane) : BLANCE_NO_NODE;   // lane sl holds row[sl]
       const int32_t* Gt = G + (size_t)top * N;
-      // nodeToNodeCounts[top] must hold every commit before step i.  The committer trails by a few hundred cycles;
-      // only an accepted step with the same top among the ones it has not reached yet makes the leader wait.
-      {
-        int cd = lds32v(cdone_a);
-        if (cd < i) {
-          bool clash = i - cd > 128;
-          for (int j0 = cd; j0 < i && !clash; j0 += 32) {
-            const int j = j0 + lane;
-            bool mine = false;
-            if (j < i) {
-              const uint32_t sj = ((((uint32_t)j >> 5) & swd_mask) << 5) | ((uint32_t)j & 31u);
-              mine = (dyn_smem[(acc_a - base_a) + sj] & 0x80u) && lds32(rec_a + sj * RECB + (uint32_t)(SLP + 2) * 4u) == top;
-            }
-            clash = __any_sync(0xFFFFFFFFu, mine);
-          }
-          if (clash) { ++n_cwait; while (lds32v(cdone_a) < i) { if (stuck(3, i, cd)) { aborted = true; break; } } spins = 0; }
-        }
-      }
-      bool retried = false;
-    resolve_again:
       bool resolved = false;
       int n_ch = 0;
       int32_t chosen[K];
 #pragma unroll
       for (int t = 0; t < K; ++t) chosen[t] = BLANCE_NO_NODE;
       bool same = false;
-      int reason = 0;
       if (row_clean && n_cur <= K) {
-        // Candidates: on lanes < n_cur a current node (with the stickiness), and my listed nodes unless a
-        // higher-priority state of the row holds them.  (A listed node that is also current needs no test: its
-        // listed key lacks the stickiness, so the current twin is picked first and takes the listed one with it -
-        // unless the stickiness is negative, then the state's own slots block too.)  The second list entry of
-        // every lane is only looked at when the K-th winner of the first round is not below lb1, a lower bound
-        // of all second entries.
-        const uint32_t blk = stick < 0.0 ? (slot_blocked | slot_state_s) : slot_blocked;
+        // candidates: my listed nodes (unless the row blocks them) and, on lanes < n_cur, a current node
         unsigned long long ck[SP_LPL + 1];
         int32_t cnode[SP_LPL + 1];
-        bool cur_ok = true;
-        auto eval = [&](int u) {                                        // exact key of candidate u (plan.go:634-689)
-          ck[u] = ~0ull;
-          if (u < SP_LPL) {
-            cnode[u] = Ln[u];
-            if (blk)
+        __syncwarp();                                                   // the commits above precede the loads below
 #pragma unroll
-              for (int sl = 0; sl < 8; ++sl)
-                if (((blk >> sl) & 1u) && rowv[sl] == Ln[u]) cnode[u] = -1;
-          } else cnode[u] = mycur;
+        for (int u = 0; u < SP_LPL; ++u) {
+          cnode[u] = Ln[u];
+          ck[u] = ~0ull;
+        }
+        {
+          const int32_t mycur = __shfl_sync(0xFFFFFFFFu, myslot, (lo_s + (lane & 7)) & 31);
+          cnode[SP_LPL] = lane < n_cur ? mycur : -1;
+        }
+        ck[SP_LPL] = ~0ull;
+        // row slots that block a listed node (it is current, or held by a higher-priority state)
+#pragma unroll
+        for (int sl = 0; sl < 8; ++sl) {
+          const int32_t x = __shfl_sync(0xFFFFFFFFu, myslot, sl);
+          if ((slot_blocked >> sl) & 1u) {
+#pragma unroll
+            for (int u = 0; u < SP_LPL; ++u) if (cnode[u] == x) cnode[u] = -1;
+          }
+        }
+        int32_t gq[SP_LPL + 1];
+#pragma unroll
+        for (int u = 0; u <= SP_LPL; ++u) gq[u] = (cnode[u] >= 0 && have_p) ? ld_relaxed_gpu(Gt + cnode[u]) : 0;
+        bool cur_ok = true;
+#pragma unroll
+        for (int u = 0; u <= SP_LPL; ++u) {
           if (cnode[u] >= 0) {
-            const int32_t g = have_p ? ld_relaxed_gpu(Gt + cnode[u]) : 0;
             const int4 ma = lds128(nd_a + (uint32_t)cnode[u] * 32u), mb = lds128(nd_a + (uint32_t)cnode[u] * 32u + 16u);
             const uint32_t fl = dyn_smem[(flg_a - base_a) + cnode[u]];
             if (u == SP_LPL && !(fl & NF_VALID)) cur_ok = false;
             ck[u] = sp_key(__hiloint2double(ma.y, ma.x), __hiloint2double(ma.w, ma.z), __hiloint2double(mb.y, mb.x),
-                           __hiloint2double(mb.w, mb.z), (fl & NF_BOOST) != 0, has_nw, g, u == SP_LPL ? stick : 0.0, have_p, Pd, Py);
+                           __hiloint2double(mb.w, mb.z), (fl & NF_BOOST) != 0, has_nw, gq[u], u == SP_LPL ? stick : 0.0, have_p, Pd, Py);
           }
-        };
-        eval(SP_LPL);
-        eval(0);
-#pragma unroll
-        for (int u = 1; u < SP_LPL; ++u) { cnode[u] = -1; ck[u] = ~0ull; }
-        SP_T(2);
+        }
         if (__all_sync(0xFFFFFFFFu, cur_ok)) {
-          const int32_t cnodeC = cnode[SP_LPL];
-          for (int round = 0; round < 2; ++round) {
-            unsigned long long lastk = 0;
-            uint32_t lastp = 0;
-            bool hit_all = true;
-            n_ch = 0;
-            uint32_t alive = 0;                                         // bit u: my candidate u is still in play
+          unsigned long long lastk = 0;
+          uint32_t lastp = 0;
+          bool hit_all = true;
+          for (int t = 0; t < K; ++t) {
+            unsigned long long bk = ~0ull;
+            uint32_t bp = 0xFFFFFFFFu;
 #pragma unroll
-            for (int u = 0; u <= SP_LPL; ++u) if (cnode[u] >= 0) alive |= 1u << u;
-            for (int t = 0; t < K; ++t) {
-              unsigned long long bk = ~0ull;
-              uint32_t bp = 0xFFFFFFFFu;
+            for (int u = 0; u <= SP_LPL; ++u)
+              if (cnode[u] >= 0 && lex_lt(ck[u], (uint32_t)cnode[u], bk, bp)) { bk = ck[u]; bp = (uint32_t)cnode[u]; }
+            const Best b = warp_argmin(Best{(uint32_t)(bk >> 32), (uint32_t)bk, bp});
+            if (b.pos == 0xFFFFFFFFu) break;
+            chosen[t] = (int32_t)b.pos;
+            ++n_ch;
+            lastk = ((unsigned long long)b.hi << 32) | b.lo;
+            lastp = b.pos;
+            const bool mine_cur = cnode[SP_LPL] == (int32_t)b.pos;
+            hit_all = hit_all && __any_sync(0xFFFFFFFFu, mine_cur);
 #pragma unroll
-              for (int u = 0; u <= SP_LPL; ++u)
-                if (((alive >> u) & 1u) && lex_lt(ck[u], (uint32_t)cnode[u], bk, bp)) { bk = ck[u]; bp = (uint32_t)cnode[u]; }
-              const Best b = warp_argmin_q(Best{(uint32_t)(bk >> 32), (uint32_t)bk, bp});
-              if (b.pos == 0xFFFFFFFFu) break;
-              chosen[t] = (int32_t)b.pos;
-              ++n_ch;
-              lastk = ((unsigned long long)b.hi << 32) | b.lo;
-              lastp = b.pos;
-              hit_all = hit_all && __any_sync(0xFFFFFFFFu, cnodeC == (int32_t)b.pos);
-#pragma unroll
-              for (int u = 0; u <= SP_LPL; ++u) if (cnode[u] == (int32_t)b.pos) alive &= ~(1u << u);
-            }
-            // could an entry of the second column be among the first K?
-            if (round == 0 && SP_LPL > 1 && !(n_ch == K && lex_lt(lastk, lastp, lb1k, lb1p))) {
-#pragma unroll
-              for (int u = 1; u < SP_LPL; ++u) eval(u);
-              ++n_round2;
-              continue;
-            }
-            const bool complete = ubp == 0xFFFFFFFFu;                    // every live node is listed
-            if (n_ch == K) { resolved = complete || lex_lt(lastk, lastp, ubk, ubp); reason = 3; }
-            else { resolved = complete; reason = 2; }
-            same = resolved && hit_all && n_ch == n_cur && n_cur == K;
-            break;
+            for (int u = 0; u <= SP_LPL; ++u) if (cnode[u] == (int32_t)b.pos) cnode[u] = -1;
           }
-        } else reason = 1;
-        SP_T(3);
+          const bool complete = ubp == 0xFFFFFFFFu;                      // every live node is listed
+          if (n_ch == K) resolved = complete || lex_lt(lastk, lastp, ubk, ubp);
+          else resolved = complete;
+          same = resolved && hit_all && n_ch == n_cur && n_cur == K;
+        }
       }
-      if (!resolved && reason == 3 && movers_since_rebuild > 0 && !retried) {
-        // the K-th winner is not provably below every unlisted node: a fresh list usually settles it
-        retried = true;
-        rebuild_list();
-        SP_T(6);
-        goto resolve_again;
-      }
+      SP_T(2);
       if (!resolved) {
         // ---- the team evaluates the step (and rebuilds the list if a count changed) ----------------------------------
         ++n_team;
-        ++why[reason];
         team_cmd(SP_OP_FULL, i);
         n_ch = *(volatile int32_t*)&ctl.res_n;
         same = *(volatile int32_t*)&ctl.res_same != 0;
@@ -951,43 +710,48 @@ __global__ void __launch_bounds__(448, 1) k_assign_pass_spec(DPool pool, int s, 
           for (int t = 0; t < K; ++t) orec[t] = chosen[t];
           orec[K] = n_ch;
         }
-        if (!same) { rebuild_list(); publish(false, 0, 0); ++n_mov; w = -64 - 64; }   // (stamps changed: reload the window)
-        SP_T(6);
+        if (!same) { adopt_list(); publish_epoch(); ++n_mov; }
+        SP_T(4);
       } else {
-        if (lane <= K) {                                               // outcome record: chosen[0..K), n_chosen
-          int32_t v = n_ch;
+        int32_t* orec = ostream + (size_t)i * REC;
+        if (lane == 0) {
 #pragma unroll
-          for (int t = 0; t < K; ++t) if (lane == t) v = chosen[t];
-          ostream[(size_t)i * REC + lane] = v;
-          if (lane < n_ch && have_p) atomicAdd(&G[(size_t)top * N + v], 1);                  // plan.go:238-245
+          for (int t = 0; t < K; ++t) orec[t] = chosen[t];
+          orec[K] = n_ch;
+        }
+        if (lane < n_ch && have_p) {
+          int32_t mine = chosen[0];
+#pragma unroll
+          for (int t = 1; t < K; ++t) if (lane == t) mine = chosen[t];
+          atomicAdd(&G[(size_t)top * N + mine], 1);                    // plan.go:238-245
         }
         if (!same) {
           // ---- a mover: lanes 0..n_cur-1 take the old nodes, lanes 8..8+n_ch-1 the new ones -------------------------
           ++n_mov;
-          ++movers_since_rebuild;
           const int32_t E1 = E + 1;
           const bool elig = n_cur == K;
           // A[top][x] changes by (x is chosen) - (the hypothesis counted x: eligible row and x current); a node whose
           // count or A entry changes is stamped, so results computed from the old values are rejected
           int delta = 0, dA = 0;
+          const int32_t oldx = __shfl_sync(0xFFFFFFFFu, myslot, (lo_s + (lane & 7)) & 31);
           int32_t newx = chosen[0];
 #pragma unroll
           for (int t = 1; t < K; ++t) if (lane - 8 == t) newx = chosen[t];
           const bool is_old = lane < n_cur, is_new = lane >= 8 && lane < 8 + n_ch;
-          const int32_t x = is_old ? mycur : (is_new ? newx : -1);
+          const int32_t x = is_old ? oldx : (is_new ? newx : -1);
           bool again = false;                   // old node that is chosen again / new node that was current
-          uint32_t memb = 0;                    // states (other than s) whose list holds my new node
           if (is_old) {
 #pragma unroll
             for (int t = 0; t < K; ++t) again = again || (t < n_ch && chosen[t] == x);
           }
-          if (is_new) {
+          uint32_t memb = 0;                    // states (other than s) whose list holds my new node
 #pragma unroll
-            for (int sl = 0; sl < 8; ++sl)
-              if (rowv[sl] == x) {
-                if ((slot_state_s >> sl) & 1u) again = true;
-                else memb |= sbit8[sl];
-              }
+          for (int sl = 0; sl < 8; ++sl) {
+            const int32_t y = __shfl_sync(0xFFFFFFFFu, myslot, sl);
+            if (is_new && y == x && sl < SLP) {
+              if ((slot_state_s >> sl) & 1u) again = true;
+              else memb |= (uint32_t)lds32(sbit_a + 4u * sl);
+            }
           }
           bool act = false;
           if (is_old && !again) { act = true; delta = -w_p; dA = elig ? -1 : 0; }
@@ -995,8 +759,9 @@ __global__ void __launch_bounds__(448, 1) k_assign_pass_spec(DPool pool, int s, 
           if (is_new && again && !elig) { act = true; dA = 1; memb = 0; }      // kept node of a short row: only A moves
           act = act && x >= 0;
           unsigned long long nk = ~0ull;
-          bool tvalid = false;
+          bool ins = false;
           if (act) {
+            if (have_p && dA) atomicAdd(&A[(size_t)top * N + x], dA);
             const int4 ma = lds128(nd_a + (uint32_t)x * 32u), mb = lds128(nd_a + (uint32_t)x * 32u + 16u);
             const uint32_t fl = dyn_smem[(flg_a - base_a) + x];
             double cd = __hiloint2double(ma.y, ma.x), ff = __hiloint2double(ma.w, ma.z);
@@ -1015,49 +780,66 @@ __global__ void __launch_bounds__(448, 1) k_assign_pass_spec(DPool pool, int s, 
             double* nd = reinterpret_cast<double*>(dyn_smem) + 4 * (size_t)x;
             nd[0] = cd; nd[1] = ff;
             sts32(chg_a + 4u * (uint32_t)x, E1);
-            nk = sp_base_key(cd, ff, __hiloint2double(mb.y, mb.x), __hiloint2double(mb.w, mb.z), (fl & NF_BOOST) != 0, has_nw);
-            *reinterpret_cast<unsigned long long*>(dyn_smem + (bk_a - base_a) + 8u * (uint32_t)x) = nk;
-            tvalid = (fl & NF_VALID) != 0;
+            nk = sp_key(cd, ff, __hiloint2double(mb.y, mb.x), __hiloint2double(mb.w, mb.z), (fl & NF_BOOST) != 0, has_nw, 0, 0.0, have_p, Pd, Py);
+            ins = (fl & NF_VALID) && lex_lt(nk, (uint32_t)x, ubk, ubp);
           }
-          SP_T(4);
-          // list: every touched node goes to its owner lane (new key in place, listed if it fell below the lane's
-          // bound); window results computed from its old state are dropped
-          const uint32_t actm = __ballot_sync(0xFFFFFFFFu, act);
-          for (uint32_t m = actm; m; m &= m - 1u) {
-            const int src = __ffs(m) - 1;
-            const int32_t tx = __shfl_sync(0xFFFFFFFFu, x, src);
-            const unsigned long long tk = __shfl_sync(0xFFFFFFFFu, nk, src);
-            const bool tv = __shfl_sync(0xFFFFFFFFu, (int)tvalid, src) != 0;
-            list_touch(tx, tk, tv);
+          __syncwarp();
+          // list: drop the touched nodes, take the ones that are (still) below ub into free places
 #pragma unroll
-            for (int u = 0; u < 2; ++u)
+          for (int u = 0; u < SP_LPL; ++u)
+            if (Ln[u] >= 0 && lds32(chg_a + 4u * (uint32_t)Ln[u]) == E1) { Ln[u] = -1; Lk[u] = ~0ull; }
+          const uint32_t insm = __ballot_sync(0xFFFFFFFFu, ins);
+          const int n_ins = __popc(insm);
+          if (n_ins) {
+            if (ins) ctl.ins[__popc(insm & ((1u << lane) - 1u))] = make_uint4((uint32_t)(nk >> 32), (uint32_t)nk, (uint32_t)x, 0u);
+            __syncwarp();
+            int placed = 0;
 #pragma unroll
-              for (int q = 0; q < K; ++q) if (cn[u][q] == tx) fresh[u] = false;
+            for (int u = 0; u < SP_LPL; ++u) {
+              const uint32_t freem = __ballot_sync(0xFFFFFFFFu, Ln[u] < 0);
+              const int r2 = placed + __popc(freem & ((1u << lane) - 1u));
+              if (Ln[u] < 0 && r2 < n_ins) {
+                const uint4 e = ctl.ins[r2];
+                Lk[u] = ((unsigned long long)e.x << 32) | e.y;
+                Ln[u] = (int32_t)e.z;
+              }
+              placed += __popc(freem);
+            }
+            for (int r2 = placed; r2 < n_ins; ++r2) {                  // no room: the node stays unlisted, ub covers it
+              const uint4 e = ctl.ins[r2];
+              const unsigned long long k = ((unsigned long long)e.x << 32) | e.y;
+              if (lex_lt(k, e.z, ubk, ubp)) { ubk = k; ubp = e.z; }
+            }
+            __syncwarp();
           }
-          publish(act && dA != 0 && have_p, (int32_t)((size_t)top * N + (x < 0 ? 0 : x)), dA);
-          recompute_b0();
-          // a list whose smallest key is no longer below ub has lost its grip on the minimum: scan the base keys again
-          if (b0_clamped && ubp != 0xFFFFFFFFu && movers_since_rebuild >= 4) { SP_T(5); rebuild_list(); SP_T(6); }
-          else SP_T(5);
+          int occ = 0;
+#pragma unroll
+          for (int u = 0; u < SP_LPL; ++u) occ += __popc(__ballot_sync(0xFFFFFFFFu, Ln[u] >= 0));
+          if (occ < SP_LMIN && ubp != 0xFFFFFFFFu) {
+            publish_epoch();
+            SP_T(3);
+            team_cmd(SP_OP_REBUILD, 0);                                 // reads the mirror only
+            adopt_list();
+            SP_T(4);
+          } else {
+            recompute_b0();
+            publish_epoch();
+            SP_T(3);
+          }
         }
       }
       ++i;
       if (lane == 0) sts32v(front_a, i);
     }
   }
-  SP_T(0);
   team_cmd(SP_OP_EXIT, 0);
-  if (lane == 0) sts32v(pubx_a, 1);
   if (lane == 0) {
     D.steps += n_assign;
     D.fast_steps += n_fast;
     D.spec_resolved += n_res; D.spec_movers += n_mov; D.spec_team += n_team; D.spec_rebuilds += n_reb;
     D.spec_waits += n_wait; D.spec_stale += n_stale;
-    cyc[7] = clock64() - t_begin;
-    for (int x = 0; x < 8; ++x) D.spec_cyc[x] += cyc[x];
-    for (int x = 0; x < 4; ++x) D.spec_why[x] += why[x];
-    D.spec_cwait += n_cwait;
-    D.spec_round2 += n_round2;
+    cyc[5] = clock64() - t_begin;
+    for (int x = 0; x < 6; ++x) D.spec_cyc[x] += cyc[x];
   }
 #undef SP_T
 }

@@ -655,12 +655,12 @@ static int run(blance_ctx* ctx, blance_plan* pl) {
       for (int i = 0; i < n; ++i) { const int kk = pl->h_insts[i].S > s ? pl->h_insts[i].state_constraints[s] : 0; if (kk >= 1 && kk <= 4) kmask |= 1u << kk; }
       // speculative kernel: 9 scout warps + the leader (warps 4 and 8 stay away from the leader's scheduler) when the
       // GPU has SMs to spare, 3 scouts per CTA for wide batches
-      // warp 0 leads, warp 1 publishes, warp 2 commits, 8 scouts (warps 4 and 8 stay away from the leader's scheduler) / 4 scouts
+      // speculative kernel: warp 0 leads, 9 scout warps (warps 4 and 8 exit at once: the leader has its scheduler to
+      // itself) when the GPU has SMs to spare; leader + 3 scouts per CTA for wide batches
       const bool spec_wide = 2 * n <= ctx->sm_count;
-      const int spec_nw = spec_wide ? 14 : 7, spec_sw = spec_wide ? 8 : 4;
-      const unsigned spec_idle = spec_wide ? ((1u << 4) | (1u << 8) | (1u << 12)) : 0u;    // scheduler 0 belongs to the leader
-      int spec_shift = 0;
-      while ((1 << spec_shift) < spec_sw * SP_D) ++spec_shift;
+      const int spec_nw = spec_wide ? 12 : 4, spec_sw = spec_wide ? 9 : 3;
+      const unsigned spec_idle = spec_wide ? ((1u << 4) | (1u << 8)) : 0u;
+      const int spec_shift = 0;
       const int spec_max_n = std::min(2048, 32 * spec_sw * SP_NPTS);
       bool any_auto = false;
       for (int i = 0; i < n; ++i) any_auto |= pl->h_insts[i].engine == BLANCE_ENGINE_AUTO;
@@ -774,9 +774,8 @@ static int fetch(blance_ctx* ctx, blance_plan* pl, blance_plan_out* outs) {
       std::fprintf(stderr, "[blance] inst %d: steps %lld accepted %lld | resolved by the leader %lld (stale results %lld) movers %lld team %lld rebuilds %lld waits %lld\n",
                    i, fin[i].steps, fin[i].fast_steps, fin[i].spec_resolved, fin[i].spec_stale, fin[i].spec_movers, fin[i].spec_team,
                    fin[i].spec_rebuilds, fin[i].spec_waits),
-      std::fprintf(stderr, "[blance]   leader cycles: scans %lld | waits %lld | resolve loads+keys %lld | picks %lld | mover mirror %lld | list+publish %lld | team %lld | passes total %lld ; team causes: unclean %lld dead %lld exhausted %lld bound %lld ; committer waits %lld ; second-column rounds %lld\n",
-                   fin[i].spec_cyc[0], fin[i].spec_cyc[1], fin[i].spec_cyc[2], fin[i].spec_cyc[3], fin[i].spec_cyc[4], fin[i].spec_cyc[5], fin[i].spec_cyc[6], fin[i].spec_cyc[7],
-                   fin[i].spec_why[0], fin[i].spec_why[1], fin[i].spec_why[2], fin[i].spec_why[3], fin[i].spec_cwait, fin[i].spec_round2);
+      std::fprintf(stderr, "[blance]   leader cycles (-DBLANCE_SPEC_TIMING builds): scans %lld | waits %lld | resolves %lld | mover updates %lld | team %lld | passes total %lld\n",
+                   fin[i].spec_cyc[0], fin[i].spec_cyc[1], fin[i].spec_cyc[2], fin[i].spec_cyc[3], fin[i].spec_cyc[4], fin[i].spec_cyc[5]);
   for (int i = 0; i < n; ++i) {
     const DInst& D = pl->h_insts[i];
     blance_plan_out& o = outs[i];
