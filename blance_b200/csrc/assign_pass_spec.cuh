@@ -43,7 +43,12 @@
 
 namespace blance_dev {
 
+#ifndef SP_LPL
 #define SP_LPL 2             // list entries per leader lane
+#endif
+#ifndef SP_MEXT
+#define SP_MEXT 7            // rebuild: entries a scout warp extracts (capped so that all fit in the list)
+#endif
 #define SP_D 2               // ring chunks per scout warp
 #define SP_NPTS 8            // nodes per scout thread in team operations (N <= 32 * SW * SP_NPTS)
 #define SP_GEN_MOD 1023      // ring generations cycle 0..1022; 1023 = never written
@@ -55,7 +60,7 @@ enum : uint32_t { SPZ_NEVER = 0x80000000u };
 
 struct SpecCtl {
   uint4 xchg[2][32];                 // team arg-min partials
-  uint4 cand[64];                    // rebuild: extracted {key hi, key lo, node, -}
+  uint4 cand[32 * SP_LPL];           // rebuild: extracted {key hi, key lo, node, -}
   uint4 bound[32];                   // rebuild: per-warp lower bound of what was not extracted
   uint4 ins[16];                     // list inserts of a mover
   alignas(16) int32_t slot_bit[BL_SLP_MAX];
@@ -236,7 +241,7 @@ __global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, 
     xbuf ^= 1;
     return warp_argmin(Best{(uint32_t)e.x, (uint32_t)e.y, (uint32_t)e.z});
   };
-  const int M_ext = (64 / SW) < 7 ? (64 / SW) : 7;       // rebuild: entries extracted per scout warp
+  const int M_ext = (32 * SP_LPL / SW) < SP_MEXT ? (32 * SP_LPL / SW) : SP_MEXT;       // rebuild: entries extracted per scout warp
 
   if (!is_leader) {
     // =================================== scouts ========================================================
@@ -507,6 +512,7 @@ __global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, 
   uint32_t ubp = 0xFFFFFFFFu, B0p = 0xFFFFFFFFu;
   int32_t E = 0;
   int seq = 0;
+  uint8_t* srank = pool.srank + D.part_off;
   long long n_fast = 0, n_res = 0, n_mov = 0, n_team = 0, n_reb = 0, n_wait = 0, n_stale = 0;
   long long cyc[6] = {0, 0, 0, 0, 0, 0}, tc = clock64();
   const long long t_begin = tc;
@@ -595,13 +601,12 @@ __global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, 
     const int run = (okm == 0xFFFFFFFFu) ? 32 : (__ffs(~okm) - 1);
     if (lane < run) {                                                   // commit: plan.go:238-245 and the step's outcome
       const int32_t top = lds32(reca + (uint32_t)(SLP + 2) * 4u);
-      int32_t* orec = ostream + (size_t)j * REC;
 #pragma unroll
-      for (int q = 0; q < K; ++q) {
+      for (int q = 0; q < K; ++q)
         if (have_p) atomicAdd(&G[(size_t)top * N + cn[q]], 1);
-        orec[((uint32_t)r.z >> (13 + 2 * q)) & 3u] = cn[q];
-      }
-      orec[K] = K;
+      // the outcome of an accepted step is "its current nodes in (score, position) order": one byte (0x80 | the
+      // ranks) in a dense array - one coalesced store per 32 steps - that k_scatter_stream expands
+      srank[j] = (uint8_t)(0x80u | (((uint32_t)r.z >> 13) & 0xFFu));
     }
     i += run;
     n_fast += run;

@@ -728,9 +728,11 @@ static int run(blance_ctx* ctx, blance_plan* pl) {
   CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]));
   pl->last_kernel_ms = ms;
   float pass = 0.f;
+  const bool show = getenv("BLANCE_PASS_TIMES") != nullptr;
   for (size_t i = 0; i + 1 < n_ev; i += 2) {
     float t = 0.f;
     if (cudaEventElapsedTime(&t, ctx->events[i], ctx->events[i + 1]) == cudaSuccess) pass += t;
+    if (show) std::fprintf(stderr, "[blance] assign pass %zu: %.3f ms\n", i / 2, t);
   }
   pl->last_pass_ms = pass;
   return BLANCE_OK;
