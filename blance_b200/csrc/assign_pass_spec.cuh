@@ -297,6 +297,12 @@ __global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, 
             uint32_t memb[SP_NPTS];
             unsigned long long key[SP_NPTS];
             uint32_t cand_bits = 0, taken_bits = 0;
+            int32_t qn[SP_NPTS];                                  // nodeToNodeCounts[top][n]: all loads in flight together
+#pragma unroll
+            for (int j = 0; j < SP_NPTS; ++j) {
+              const int n = team_node(j);
+              qn[j] = (have_p && n < N) ? ld_relaxed_gpu(G + (size_t)top * N + n) : 0;
+            }
 #pragma unroll
             for (int j = 0; j < SP_NPTS; ++j) {
               const int n = team_node(j);
@@ -307,7 +313,7 @@ __global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, 
                   if (lds32(reca + 4u * sl) == n) memb[j] |= (uint32_t)lds32(sbit_a + 4u * sl);
                 const int4 ma = lds128(nd_a + (uint32_t)n * 32u), mb = lds128(nd_a + (uint32_t)n * 32u + 16u);
                 const uint32_t fl = dyn_smem[(flg_a - base_a) + n];
-                const int32_t q = have_p ? ld_relaxed_gpu(G + (size_t)top * N + n) : 0;
+                const int32_t q = qn[j];
                 const bool cand = (fl & NF_VALID) && !(memb[j] & higher_states);           // plan.go:142-156
                 const double cur = ((memb[j] >> s) & 1u) ? stick : 0.0;                    // plan.go:654-662
                 if (cand) {
@@ -463,9 +469,12 @@ __global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, 
           const int32_t qsv[4] = {qs.x, qs.y, qs.z, qs.w};
           unsigned long long key[K];
           bool ok = true;
+          int32_t av[K];                                        // (all loads in flight together: one L2 round trip)
+#pragma unroll
+          for (int q = 0; q < K; ++q) av[q] = have_p ? ld_relaxed_gpu(A + (size_t)top * N + cn[q]) : 0;
 #pragma unroll
           for (int q = 0; q < K; ++q) {
-            const int32_t a = have_p ? ld_relaxed_gpu(A + (size_t)top * N + cn[q]) : 0;
+            const int32_t a = av[q];
             const int4 ma = lds128(nd_a + (uint32_t)cn[q] * 32u), mb2 = lds128(nd_a + (uint32_t)cn[q] * 32u + 16u);
             const uint32_t fl = dyn_smem[(flg_a - base_a) + cn[q]];
             ok = ok && (fl & NF_VALID);
