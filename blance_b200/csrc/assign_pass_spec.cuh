@@ -52,7 +52,15 @@ namespace blance_dev {
 #define SP_D 2               // ring chunks per scout warp
 #define SP_NPTS 8            // nodes per scout thread in team operations (N <= 32 * SW * SP_NPTS)
 #define SP_GEN_MOD 1023      // ring generations cycle 0..1022; 1023 = never written
-#define SP_LMIN 10           // rebuild the list when fewer entries are left (and it is not complete)
+#ifndef SP_LB
+#define SP_LB 544            // launch bound (the register budget follows from it: 544 -> 96, 512 -> 128, 384 -> 168)
+#endif
+#ifndef SP_U
+#define SP_U 1               // groups of 32 steps the leader examines per scan (independent instruction streams)
+#endif
+#ifndef SP_LMIN
+#define SP_LMIN 4            // rebuild the list when fewer entries are left (and it is not complete)
+#endif
 
 enum : int { SPB_ALL = 8, SPB_GO = 9, SPB_DONE = 10, SPB_TEAM = 11 };
 enum : int32_t { SP_OP_EXIT = 1, SP_OP_REBUILD = 2, SP_OP_FULL = 3 };
@@ -131,7 +139,7 @@ __device__ __forceinline__ bool lex_lt(unsigned long long ka, uint32_t pa, unsig
 // K = the state's constraints (1..BL_FAST_K).  blockDim.x = 32 * NW warps; warp 0 is the leader, the warps
 // of idle_mask exit at once (they keep the leader's scheduler free), the others are the SW scouts.
 template <int K>
-__global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, int SW, unsigned idle_mask, int /*unused*/) {
+__global__ void __launch_bounds__(SP_LB, 1) k_assign_pass_spec(DPool pool, int s, int SW, unsigned idle_mask, int /*unused*/) {
   DInst& D = pool.insts[blockIdx.x];
   if (!D.active || s >= D.S || D.pass_mode != 2) return;
   if (D.state_constraints[s] != K) return;
@@ -297,6 +305,19 @@ __global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, 
             uint32_t memb[SP_NPTS];
             unsigned long long key[SP_NPTS];
             uint32_t cand_bits = 0, taken_bits = 0;
+            int32_t frow[8];                                      // the row and the state bit of every slot, once
+            uint32_t fbit[8];
+            {
+              const int4 r0 = lds128(reca);
+              const int4 r1 = SLP > 4 ? lds128(reca + 16u) : make_int4(BLANCE_NO_NODE, BLANCE_NO_NODE, BLANCE_NO_NODE, BLANCE_NO_NODE);
+              frow[0] = r0.x; frow[1] = r0.y; frow[2] = r0.z; frow[3] = r0.w;
+              frow[4] = r1.x; frow[5] = r1.y; frow[6] = r1.z; frow[7] = r1.w;
+#pragma unroll
+              for (int sl = 0; sl < 8; ++sl) {
+                fbit[sl] = sl < SLP ? (uint32_t)lds32(sbit_a + 4u * sl) : 0u;
+                if (sl >= SLP) frow[sl] = -2;                     // (never a node id)
+              }
+            }
             int32_t qn[SP_NPTS];                                  // nodeToNodeCounts[top][n]: all loads in flight together
 #pragma unroll
             for (int j = 0; j < SP_NPTS; ++j) {
@@ -309,8 +330,9 @@ __global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, 
               memb[j] = 0;
               key[j] = ~0ull;
               if (n < N) {
-                for (int sl = 0; sl < SLP; ++sl)
-                  if (lds32(reca + 4u * sl) == n) memb[j] |= (uint32_t)lds32(sbit_a + 4u * sl);
+#pragma unroll
+                for (int sl = 0; sl < 8; ++sl)
+                  if (frow[sl] == n) memb[j] |= fbit[sl];
                 const int4 ma = lds128(nd_a + (uint32_t)n * 32u), mb = lds128(nd_a + (uint32_t)n * 32u + 16u);
                 const uint32_t fl = dyn_smem[(flg_a - base_a) + n];
                 const int32_t q = qn[j];
@@ -585,51 +607,73 @@ __global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, 
   SP_T(4);
 
   int i = 0;
+  uint32_t cslot = 0, cgen = 0;
   while (i < n_assign) {
-    // ---- a group of 32 steps: accept the leading run of results that are still exact and sticky ----------------
-    const int j = i + lane;
-    const int cj = j >> 5;
-    const uint32_t slot = (uint32_t)(cj % SWD) * 32u + (uint32_t)(j & 31);
-    const uint32_t gen = (uint32_t)((cj / SWD) % SP_GEN_MOD);
-    const uint32_t reca = rec_a + slot * RECB;
-    const int4 r = lds128(dyn_a + slot * 16u);
-    int32_t cn[K];
+    // ---- SP_U groups of 32 steps: accept the leading run of results that are still exact and sticky --------------
+    // (the ring slot and the generation of step i's chunk are carried along - cslot = (i >> 5) % SWD, cgen =
+    // (i >> 5) / SWD % SP_GEN_MOD; the groups are independent instruction streams, which is what a lone warp needs)
+    int4 r[SP_U];
+    int32_t cn[SP_U][K];
+    uint32_t reca[SP_U], okm[SP_U];
+    bool have[SP_U], never[SP_U], fresh[SP_U];
 #pragma unroll
-    for (int q = 0; q < K; ++q) cn[q] = lds32(reca + (uint32_t)(lo_s + q) * 4u);
-    const bool live = j < n_assign;
-    const bool have = live && (((uint32_t)r.z >> 21) & 0x3FFu) == gen;
-    const bool never = ((uint32_t)r.z & SPZ_NEVER) != 0;
-    bool fresh = have && !never;
-    if (fresh) {
+    for (int g = 0; g < SP_U; ++g) {
+      const int j = i + 32 * g + lane;
+      const uint32_t adv = (uint32_t)((i & 31) + lane + 32 * g) >> 5;   // chunks ahead of step i's (<= SP_U < SWD)
+      uint32_t jslot = cslot + adv, gen = cgen;
+      if (jslot >= (uint32_t)SWD) { jslot -= (uint32_t)SWD; if (++gen == (uint32_t)SP_GEN_MOD) gen = 0; }
+      const uint32_t slot = jslot * 32u + (uint32_t)(j & 31);
+      reca[g] = rec_a + slot * RECB;
+      r[g] = lds128(dyn_a + slot * 16u);
 #pragma unroll
-      for (int q = 0; q < K; ++q) fresh = fresh && lds32(chg_a + 4u * (uint32_t)cn[q]) <= r.w;
+      for (int q = 0; q < K; ++q) cn[g][q] = lds32(reca[g] + (uint32_t)(lo_s + q) * 4u);
+      have[g] = j < n_assign && (((uint32_t)r[g].z >> 21) & 0x3FFu) == gen;
+      never[g] = ((uint32_t)r[g].z & SPZ_NEVER) != 0;
     }
-    const unsigned long long T = ((unsigned long long)(uint32_t)r.x << 32) | (uint32_t)r.y;
-    const bool ok = fresh && lex_lt(T, (uint32_t)r.z & 0x1FFFu, B0k, B0p);
-    const uint32_t okm = __ballot_sync(0xFFFFFFFFu, ok);
-    const int run = (okm == 0xFFFFFFFFu) ? 32 : (__ffs(~okm) - 1);
-    if (lane < run) {                                                   // commit: plan.go:238-245 and the step's outcome
-      const int32_t top = lds32(reca + (uint32_t)(SLP + 2) * 4u);
 #pragma unroll
-      for (int q = 0; q < K; ++q)
-        if (have_p) atomicAdd(&G[(size_t)top * N + cn[q]], 1);
-      // the outcome of an accepted step is "its current nodes in (score, position) order": one byte (0x80 | the
-      // ranks) in a dense array - one coalesced store per 32 steps - that k_scatter_stream expands
-      srank[j] = (uint8_t)(0x80u | (((uint32_t)r.z >> 13) & 0xFFu));
+    for (int g = 0; g < SP_U; ++g) {
+      fresh[g] = have[g] && !never[g];
+      int32_t lc[K];
+#pragma unroll
+      for (int q = 0; q < K; ++q) lc[q] = fresh[g] ? lds32(chg_a + 4u * (uint32_t)cn[g][q]) : 0;
+#pragma unroll
+      for (int q = 0; q < K; ++q) fresh[g] = fresh[g] && lc[q] <= r[g].w;
+      const unsigned long long T = ((unsigned long long)(uint32_t)r[g].x << 32) | (uint32_t)r[g].y;
+      okm[g] = __ballot_sync(0xFFFFFFFFu, fresh[g] && lex_lt(T, (uint32_t)r[g].z & 0x1FFFu, B0k, B0p));
     }
+    int run = 0;
+#pragma unroll
+    for (int g = SP_U - 1; g >= 0; --g) run = (okm[g] == 0xFFFFFFFFu) ? 32 + run : (__ffs(~okm[g]) - 1);
+#pragma unroll
+    for (int g = 0; g < SP_U; ++g) {
+      if (32 * g + lane < run) {                                        // commit: plan.go:238-245 and the step's outcome
+        const int32_t top = lds32(reca[g] + (uint32_t)(SLP + 2) * 4u);
+#pragma unroll
+        for (int q = 0; q < K; ++q)
+          if (have_p) atomicAdd(&G[(size_t)top * N + cn[g][q]], 1);
+        // the outcome of an accepted step is "its current nodes in (score, position) order": one byte (0x80 | the
+        // ranks) in a dense array - one coalesced store per 32 steps - that k_scatter_stream expands
+        srank[i + 32 * g + lane] = (uint8_t)(0x80u | (((uint32_t)r[g].z >> 13) & 0xFFu));
+      }
+    }
+    cslot += (uint32_t)((i & 31) + run) >> 5;                           // i moves on by up to SP_U chunks
+    if (cslot >= (uint32_t)SWD) { cslot -= (uint32_t)SWD; if (++cgen == (uint32_t)SP_GEN_MOD) cgen = 0; }
     i += run;
     n_fast += run;
     if (run > 0 && lane == 0) sts32v(front_a, i);
     SP_T(0);
-    if (run == 32 || i >= n_assign) continue;
+    if (run == 32 * SP_U || i >= n_assign) continue;
     // ---- step i was not accepted -----------------------------------------------------------------------------------
-    const bool have_i = __shfl_sync(0xFFFFFFFFu, (int)have, run) != 0;
+    bool have_l = have[0], stale_l = have[0] && !never[0] && !fresh[0];
+#pragma unroll
+    for (int g = 1; g < SP_U; ++g)
+      if ((run >> 5) == g) { have_l = have[g]; stale_l = have[g] && !never[g] && !fresh[g]; }
+    const bool have_i = __shfl_sync(0xFFFFFFFFu, (int)have_l, run & 31) != 0;
     if (!have_i) { ++n_wait; if (run == 0) __nanosleep(100); SP_T(1); continue; }        // its scout has not got there yet
-    if (__shfl_sync(0xFFFFFFFFu, (int)(have && !never && !fresh), run)) ++n_stale;
+    if (__shfl_sync(0xFFFFFFFFu, (int)stale_l, run & 31)) ++n_stale;
     ++n_res;
     {
-      const int ci = i >> 5;
-      const uint32_t slot_i = (uint32_t)(ci % SWD) * 32u + (uint32_t)(i & 31);
+      const uint32_t slot_i = cslot * 32u + (uint32_t)(i & 31);
       const uint32_t rb = rec_a + slot_i * RECB;
       const int4 hdr = lds128(rb + (uint32_t)SLP * 4u);               // meta, w_p, top, partition
       const int32_t w_p = hdr.y, top = hdr.z;
@@ -654,10 +698,8 @@ __global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, 
           cnode[u] = Ln[u];
           ck[u] = ~0ull;
         }
-        {
-          const int32_t mycur = __shfl_sync(0xFFFFFFFFu, myslot, (lo_s + (lane & 7)) & 31);
-          cnode[SP_LPL] = lane < n_cur ? mycur : -1;
-        }
+        const int32_t mycur = __shfl_sync(0xFFFFFFFFu, myslot, (lo_s + (lane & 7)) & 31);
+        cnode[SP_LPL] = lane < n_cur ? mycur : -1;
         ck[SP_LPL] = ~0ull;
         // row slots that block a listed node (it is current, or held by a higher-priority state)
 #pragma unroll
@@ -706,6 +748,17 @@ __global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, 
           const bool complete = ubp == 0xFFFFFFFFu;                      // every live node is listed
           if (n_ch == K) resolved = complete || lex_lt(lastk, lastp, ubk, ubp);
           else resolved = complete;
+#ifdef BLANCE_SPEC_DIAG
+          if (!resolved && D.debug && blockIdx.x == 0 && n_team < 24) {      // what do the failed proofs look like?
+            int occ_ = 0;
+#pragma unroll
+            for (int u = 0; u < SP_LPL; ++u) occ_ += __popc(__ballot_sync(0xFFFFFFFFu, Ln[u] >= 0));
+            const bool last_is_cur = __any_sync(0xFFFFFFFFu, lane < n_cur && mycur == (int32_t)lastp);
+            if (lane == 0)
+              printf("[blance] bound fail at step %d: K %d n_cur %d n_ch %d last %u (%s) key %llx ub %llx (node %u) B0 %llx listed %d hit_all %d\n",
+                     i, K, n_cur, n_ch, lastp, last_is_cur ? "current" : "listed", lastk, ubk, ubp, B0k, occ_, (int)hit_all);
+          }
+#endif
           same = resolved && hit_all && n_ch == n_cur && n_cur == K;
         }
       }
@@ -842,7 +895,9 @@ __global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, 
           }
         }
       }
-      ++i;
+      if ((++i & 31) == 0) {
+        if (++cslot == (uint32_t)SWD) { cslot = 0; if (++cgen == (uint32_t)SP_GEN_MOD) cgen = 0; }
+      }
       if (lane == 0) sts32v(front_a, i);
     }
   }
@@ -852,6 +907,11 @@ __global__ void __launch_bounds__(544, 1) k_assign_pass_spec(DPool pool, int s, 
     D.fast_steps += n_fast;
     D.spec_resolved += n_res; D.spec_movers += n_mov; D.spec_team += n_team; D.spec_rebuilds += n_reb;
     D.spec_waits += n_wait; D.spec_stale += n_stale;
+#ifdef BLANCE_SPEC_DIAG
+    if (D.debug && blockIdx.x == 0)
+      printf("[blance] spec pass state %d K %d: steps %d accepted %lld resolved %lld movers %lld team %lld rebuilds %lld stale %lld waits %lld\n",
+             s, K, n_assign, n_fast, n_res, n_mov, n_team, n_reb, n_stale, n_wait);
+#endif
     cyc[5] = clock64() - t_begin;
     for (int x = 0; x < 6; ++x) D.spec_cyc[x] += cyc[x];
   }

@@ -292,6 +292,7 @@ static int upload(blance_ctx* ctx, int n, const blance_plan_in* ins, blance_plan
     D.top_state = in.top_state; D.booster = in.booster_kind;
     D.has_part_weights = in.has_part_weights; D.has_node_weights = in.has_node_weights;
     D.has_hier_rules = in.has_hier_rules; D.max_iters = in.max_iters; D.engine = in.engine;
+    D.debug = getenv("BLANCE_SPEC_STATS") ? 1 : 0;
     for (int s = 0; s < in.n_states; ++s) {
       D.state_priority[s] = in.state_priority[s];
       D.state_constraints[s] = in.state_constraints[s];

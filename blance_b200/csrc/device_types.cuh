@@ -38,6 +38,7 @@ struct DInst {
   int32_t N, NU, S, PU, SL, SLP, HW, n_rules;
   int32_t top_state, booster, has_part_weights, has_node_weights, has_hier_rules;
   int32_t max_iters, n_assign, n_valid, engine;
+  int32_t debug;           // BLANCE_SPEC_STATS: the speculative kernel prints its counters after every pass
   int32_t state_priority[BL_S_MAX], state_constraints[BL_S_MAX], state_slot_off[BL_S_MAX + 1];
   int32_t state_stickiness[BL_S_MAX], state_has_stickiness[BL_S_MAX], rule_off[BL_S_MAX + 1];
   // offsets (in elements) into the pooled arrays
