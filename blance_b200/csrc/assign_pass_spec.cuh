@@ -575,11 +575,6 @@ __global__ void __launch_bounds__(SP_LB, 1) k_assign_pass_spec(DPool pool, int s
     if (b.pos != 0xFFFFFFFFu) { B0k = ((unsigned long long)b.hi << 32) | b.lo; B0p = b.pos; }
     else { B0k = ubk; B0p = ubp; }
   };
-  // entry e = lane + 32 u of the list takes the (e / SW)-th smallest key of scout e % SW: the keys most likely to be
-  // below the common bound land in column 0, so that column 1 is often empty (and skipped by the resolve)
-  int aix[SP_LPL];
-#pragma unroll
-  for (int u = 0; u < SP_LPL; ++u) { const int e = lane + 32 * u; aix[u] = (e % SW) * M_ext + e / SW; }
   auto adopt_list = [&]() {                 // after a team rebuild: cand[] / bound[] -> list, ub, B0
     uint4 bb = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);
     if (lane < SW) bb = ctl.bound[lane];
@@ -592,7 +587,7 @@ __global__ void __launch_bounds__(SP_LB, 1) k_assign_pass_spec(DPool pool, int s
       Lk[u] = ~0ull; Ln[u] = -1;
       const int x = lane + 32 * u;
       if (x < n_cand) {
-        const uint4 c = ctl.cand[aix[u]];
+        const uint4 c = ctl.cand[x];
         const unsigned long long k = ((unsigned long long)c.x << 32) | c.y;
         if (c.z != 0xFFFFFFFFu && lex_lt(k, c.z, ubk, ubp)) { Lk[u] = k; Ln[u] = (int32_t)c.z; }
       }
@@ -703,7 +698,8 @@ __global__ void __launch_bounds__(SP_LB, 1) k_assign_pass_spec(DPool pool, int s
           cnode[u] = Ln[u];
           ck[u] = ~0ull;
         }
-        cnode[SP_LPL] = -1;
+        const int32_t mycur = __shfl_sync(0xFFFFFFFFu, myslot, (lo_s + (lane & 7)) & 31);
+        cnode[SP_LPL] = lane < n_cur ? mycur : -1;
         ck[SP_LPL] = ~0ull;
         // row slots that block a listed node (it is current, or held by a higher-priority state)
 #pragma unroll
@@ -714,39 +710,18 @@ __global__ void __launch_bounds__(SP_LB, 1) k_assign_pass_spec(DPool pool, int s
             for (int u = 0; u < SP_LPL; ++u) if (cnode[u] == x) cnode[u] = -1;
           }
         }
-        // the current nodes ride in free places of the first list column that has room for them (a column costs the
-        // same whether 2 or 32 of its lanes are live, and a column without a live lane is skipped)
-        uint32_t curm = 0;                                              // bit u: my candidate of column u is a current node
-        {
-          bool placed = n_cur == 0;
-#pragma unroll
-          for (int u = 0; u <= SP_LPL; ++u) {
-            const uint32_t freem = __ballot_sync(0xFFFFFFFFu, cnode[u] < 0);
-            const int r2 = __popc(freem & ((1u << lane) - 1u));
-            const int32_t cq = __shfl_sync(0xFFFFFFFFu, myslot, (lo_s + (r2 & 7)) & 31);
-            if (!placed && __popc(freem) >= n_cur) {
-              placed = true;
-              if (cnode[u] < 0 && r2 < n_cur) { cnode[u] = cq; curm |= 1u << u; }
-            }
-          }
-        }
-        uint32_t livem = 0;                                             // bit u: column u has a live lane
-#pragma unroll
-        for (int u = 0; u <= SP_LPL; ++u) livem |= __any_sync(0xFFFFFFFFu, cnode[u] >= 0) ? 1u << u : 0u;
         int32_t gq[SP_LPL + 1];
 #pragma unroll
         for (int u = 0; u <= SP_LPL; ++u) gq[u] = (cnode[u] >= 0 && have_p) ? ld_relaxed_gpu(Gt + cnode[u]) : 0;
         bool cur_ok = true;
 #pragma unroll
         for (int u = 0; u <= SP_LPL; ++u) {
-          if (!((livem >> u) & 1u)) continue;
           if (cnode[u] >= 0) {
-            const bool isc = (curm >> u) & 1u;
             const int4 ma = lds128(nd_a + (uint32_t)cnode[u] * 32u), mb = lds128(nd_a + (uint32_t)cnode[u] * 32u + 16u);
             const uint32_t fl = dyn_smem[(flg_a - base_a) + cnode[u]];
-            if (isc && !(fl & NF_VALID)) cur_ok = false;
+            if (u == SP_LPL && !(fl & NF_VALID)) cur_ok = false;
             ck[u] = sp_key(__hiloint2double(ma.y, ma.x), __hiloint2double(ma.w, ma.z), __hiloint2double(mb.y, mb.x),
-                           __hiloint2double(mb.w, mb.z), (fl & NF_BOOST) != 0, has_nw, gq[u], isc ? stick : 0.0, have_p, Pd, Py);
+                           __hiloint2double(mb.w, mb.z), (fl & NF_BOOST) != 0, has_nw, gq[u], u == SP_LPL ? stick : 0.0, have_p, Pd, Py);
           }
         }
         if (__all_sync(0xFFFFFFFFu, cur_ok)) {
@@ -765,9 +740,7 @@ __global__ void __launch_bounds__(SP_LB, 1) k_assign_pass_spec(DPool pool, int s
             ++n_ch;
             lastk = ((unsigned long long)b.hi << 32) | b.lo;
             lastp = b.pos;
-            bool mine_cur = false;
-#pragma unroll
-            for (int u = 0; u <= SP_LPL; ++u) mine_cur = mine_cur || (((curm >> u) & 1u) && cnode[u] == (int32_t)b.pos);
+            const bool mine_cur = cnode[SP_LPL] == (int32_t)b.pos;
             hit_all = hit_all && __any_sync(0xFFFFFFFFu, mine_cur);
 #pragma unroll
             for (int u = 0; u <= SP_LPL; ++u) if (cnode[u] == (int32_t)b.pos) cnode[u] = -1;
@@ -780,7 +753,7 @@ __global__ void __launch_bounds__(SP_LB, 1) k_assign_pass_spec(DPool pool, int s
             int occ_ = 0;
 #pragma unroll
             for (int u = 0; u < SP_LPL; ++u) occ_ += __popc(__ballot_sync(0xFFFFFFFFu, Ln[u] >= 0));
-            const bool last_is_cur = false;
+            const bool last_is_cur = __any_sync(0xFFFFFFFFu, lane < n_cur && mycur == (int32_t)lastp);
             if (lane == 0)
               printf("[blance] bound fail at step %d: K %d n_cur %d n_ch %d last %u (%s) key %llx ub %llx (node %u) B0 %llx listed %d hit_all %d\n",
                      i, K, n_cur, n_ch, lastp, last_is_cur ? "current" : "listed", lastk, ubk, ubp, B0k, occ_, (int)hit_all);
