@@ -52,8 +52,12 @@ namespace blance_dev {
 #define SP_D 2               // ring chunks per scout warp
 #define SP_NPTS 8            // nodes per scout thread in team operations (N <= 32 * SW * SP_NPTS)
 #define SP_GEN_MOD 1023      // ring generations cycle 0..1022; 1023 = never written
+#ifndef SP_IDLE_NS
+#define SP_IDLE_NS 500       // a scout with nothing to do sleeps this long between looks at the leader's words
+#define SP_BUSY_NS 100
+#endif
 #ifndef SP_LB
-#define SP_LB 544            // launch bound (the register budget follows from it: 544 -> 96, 512 -> 128, 384 -> 168)
+#define SP_LB 512            // launch bound (the register budget follows from it: 544 -> 96, 512 -> 128, 384 -> 168)
 #endif
 #ifndef SP_U
 #define SP_U 1               // groups of 32 steps the leader examines per scan (independent instruction streams)
@@ -325,24 +329,36 @@ __global__ void __launch_bounds__(SP_LB, 1) k_assign_pass_spec(DPool pool, int s
               qn[j] = (have_p && n < N) ? ld_relaxed_gpu(G + (size_t)top * N + n) : 0;
             }
 #pragma unroll
-            for (int j = 0; j < SP_NPTS; ++j) {
-              const int n = team_node(j);
-              memb[j] = 0;
-              key[j] = ~0ull;
-              if (n < N) {
+            for (int j = 0; j < SP_NPTS; ++j) { memb[j] = 0; key[j] = ~0ull; }
+            // four node slots at a time, branch-free: four independent FP64 chains per thread in flight
+#pragma unroll
+            for (int h = 0; h < SP_NPTS; h += 4) {
+              if (SW * 32 * h >= N) break;                                                 // (uniform)
+              int4 ma[4], mb[4];
+              uint32_t fl[4];
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const int n = team_node(h + jj);
+                const uint32_t nx = n < N ? (uint32_t)n : 0u;
+                ma[jj] = lds128(nd_a + nx * 32u);
+                mb[jj] = lds128(nd_a + nx * 32u + 16u);
+                fl[jj] = dyn_smem[(flg_a - base_a) + nx];
+              }
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const int j = h + jj;
+                const int n = team_node(j);
+                uint32_t mm = 0;
 #pragma unroll
                 for (int sl = 0; sl < 8; ++sl)
-                  if (frow[sl] == n) memb[j] |= fbit[sl];
-                const int4 ma = lds128(nd_a + (uint32_t)n * 32u), mb = lds128(nd_a + (uint32_t)n * 32u + 16u);
-                const uint32_t fl = dyn_smem[(flg_a - base_a) + n];
-                const int32_t q = qn[j];
-                const bool cand = (fl & NF_VALID) && !(memb[j] & higher_states);           // plan.go:142-156
-                const double cur = ((memb[j] >> s) & 1u) ? stick : 0.0;                    // plan.go:654-662
-                if (cand) {
-                  key[j] = sp_key(__hiloint2double(ma.y, ma.x), __hiloint2double(ma.w, ma.z), __hiloint2double(mb.y, mb.x),
-                                  __hiloint2double(mb.w, mb.z), (fl & NF_BOOST) != 0, has_nw, q, cur, have_p, Pd, Py);
-                  cand_bits |= 1u << j;
-                }
+                  if (frow[sl] == n) mm |= fbit[sl];
+                const bool cand = n < N && (fl[jj] & NF_VALID) && !(mm & higher_states);   // plan.go:142-156
+                const double cur = ((mm >> s) & 1u) ? stick : 0.0;                         // plan.go:654-662
+                const unsigned long long k =
+                    sp_key(__hiloint2double(ma[jj].y, ma[jj].x), __hiloint2double(ma[jj].w, ma[jj].z), __hiloint2double(mb[jj].y, mb[jj].x),
+                           __hiloint2double(mb[jj].w, mb[jj].z), (fl[jj] & NF_BOOST) != 0, has_nw, qn[j], cur, have_p, Pd, Py);
+                if (n < N) memb[j] = mm;
+                if (cand) { key[j] = k; cand_bits |= 1u << j; }
               }
             }
             int n_chosen = 0;
@@ -406,15 +422,27 @@ __global__ void __launch_bounds__(SP_LB, 1) k_assign_pass_spec(DPool pool, int s
             unsigned long long bkey[SP_NPTS];
             uint32_t live = 0;
 #pragma unroll
-            for (int j = 0; j < SP_NPTS; ++j) {
-              const int n = team_node(j);
-              bkey[j] = ~0ull;
-              if (n < N && (dyn_smem[(flg_a - base_a) + n] & NF_VALID)) {
-                const int4 ma = lds128(nd_a + (uint32_t)n * 32u), mb = lds128(nd_a + (uint32_t)n * 32u + 16u);
-                const uint32_t fl = dyn_smem[(flg_a - base_a) + n];
-                bkey[j] = sp_key(__hiloint2double(ma.y, ma.x), __hiloint2double(ma.w, ma.z), __hiloint2double(mb.y, mb.x),
-                                 __hiloint2double(mb.w, mb.z), (fl & NF_BOOST) != 0, has_nw, 0, 0.0, have_p, Pd, Py);
-                live |= 1u << j;
+            for (int j = 0; j < SP_NPTS; ++j) bkey[j] = ~0ull;
+#pragma unroll
+            for (int h = 0; h < SP_NPTS; h += 4) {
+              if (SW * 32 * h >= N) break;                                                 // (uniform)
+              int4 ma[4], mb[4];
+              uint32_t fl[4];
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const int n = team_node(h + jj);
+                const uint32_t nx = n < N ? (uint32_t)n : 0u;
+                ma[jj] = lds128(nd_a + nx * 32u);
+                mb[jj] = lds128(nd_a + nx * 32u + 16u);
+                fl[jj] = dyn_smem[(flg_a - base_a) + nx];
+              }
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const int j = h + jj;
+                const unsigned long long k =
+                    sp_key(__hiloint2double(ma[jj].y, ma[jj].x), __hiloint2double(ma[jj].w, ma[jj].z), __hiloint2double(mb[jj].y, mb[jj].x),
+                           __hiloint2double(mb[jj].w, mb[jj].z), (fl[jj] & NF_BOOST) != 0, has_nw, 0, 0.0, have_p, Pd, Py);
+                if (team_node(j) < N && (fl[jj] & NF_VALID)) { bkey[j] = k; live |= 1u << j; }
               }
             }
             for (int r = 0; r <= M_ext; ++r) {
@@ -525,8 +553,8 @@ __global__ void __launch_bounds__(SP_LB, 1) k_assign_pass_spec(DPool pool, int s
         __threadfence_block();                          // the record (TMA) and my reads are ordered before the result
         if (live) sts128(dyn_a + slot * 16u, (uint32_t)(T >> 32), (uint32_t)T, z, (uint32_t)e);
       }
-      if (!any_work) __nanosleep(500);
-      else if (!busy) __nanosleep(100);
+      if (!any_work) __nanosleep(SP_IDLE_NS);
+      else if (!busy) __nanosleep(SP_BUSY_NS);
     }
   scouts_done:
     // ---- write the per-node counts of this state back ------------------------------------------------------
@@ -714,14 +742,25 @@ __global__ void __launch_bounds__(SP_LB, 1) k_assign_pass_spec(DPool pool, int s
 #pragma unroll
         for (int u = 0; u <= SP_LPL; ++u) gq[u] = (cnode[u] >= 0 && have_p) ? ld_relaxed_gpu(Gt + cnode[u]) : 0;
         bool cur_ok = true;
+        {
+          // branch-free over the columns: independent FP64 chains that the scheduler can interleave (a lone warp pays
+          // the full latency of every dependent instruction, so the three columns one after the other cost three chains)
+          int4 ma[SP_LPL + 1], mb[SP_LPL + 1];
+          uint32_t fl[SP_LPL + 1];
 #pragma unroll
-        for (int u = 0; u <= SP_LPL; ++u) {
-          if (cnode[u] >= 0) {
-            const int4 ma = lds128(nd_a + (uint32_t)cnode[u] * 32u), mb = lds128(nd_a + (uint32_t)cnode[u] * 32u + 16u);
-            const uint32_t fl = dyn_smem[(flg_a - base_a) + cnode[u]];
-            if (u == SP_LPL && !(fl & NF_VALID)) cur_ok = false;
-            ck[u] = sp_key(__hiloint2double(ma.y, ma.x), __hiloint2double(ma.w, ma.z), __hiloint2double(mb.y, mb.x),
-                           __hiloint2double(mb.w, mb.z), (fl & NF_BOOST) != 0, has_nw, gq[u], u == SP_LPL ? stick : 0.0, have_p, Pd, Py);
+          for (int u = 0; u <= SP_LPL; ++u) {
+            const uint32_t nx = cnode[u] >= 0 ? (uint32_t)cnode[u] : 0u;
+            ma[u] = lds128(nd_a + nx * 32u);
+            mb[u] = lds128(nd_a + nx * 32u + 16u);
+            fl[u] = dyn_smem[(flg_a - base_a) + nx];
+          }
+          if (cnode[SP_LPL] >= 0 && !(fl[SP_LPL] & NF_VALID)) cur_ok = false;
+#pragma unroll
+          for (int u = 0; u <= SP_LPL; ++u) {
+            const unsigned long long k =
+                sp_key(__hiloint2double(ma[u].y, ma[u].x), __hiloint2double(ma[u].w, ma[u].z), __hiloint2double(mb[u].y, mb[u].x),
+                       __hiloint2double(mb[u].w, mb[u].z), (fl[u] & NF_BOOST) != 0, has_nw, gq[u], u == SP_LPL ? stick : 0.0, have_p, Pd, Py);
+            ck[u] = cnode[u] >= 0 ? k : ~0ull;
           }
         }
         if (__all_sync(0xFFFFFFFFu, cur_ok)) {
