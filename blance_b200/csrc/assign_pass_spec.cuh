@@ -643,6 +643,7 @@ __global__ void __launch_bounds__(SP_LB, 1) k_assign_pass_spec(DPool pool, int s
     int4 r[SP_U];
     int32_t cn[SP_U][K];
     uint32_t reca[SP_U], okm[SP_U];
+    int32_t top[SP_U];
     bool have[SP_U], never[SP_U], fresh[SP_U];
 #pragma unroll
     for (int g = 0; g < SP_U; ++g) {
@@ -655,6 +656,7 @@ __global__ void __launch_bounds__(SP_LB, 1) k_assign_pass_spec(DPool pool, int s
       r[g] = lds128(dyn_a + slot * 16u);
 #pragma unroll
       for (int q = 0; q < K; ++q) cn[g][q] = lds32(reca[g] + (uint32_t)(lo_s + q) * 4u);
+      top[g] = lds32(reca[g] + (uint32_t)(SLP + 2) * 4u);               // (for the commit: not behind the ballot)
       have[g] = j < n_assign && (((uint32_t)r[g].z >> 21) & 0x3FFu) == gen;
       never[g] = ((uint32_t)r[g].z & SPZ_NEVER) != 0;
     }
@@ -669,16 +671,22 @@ __global__ void __launch_bounds__(SP_LB, 1) k_assign_pass_spec(DPool pool, int s
       const unsigned long long T = ((unsigned long long)(uint32_t)r[g].x << 32) | (uint32_t)r[g].y;
       okm[g] = __ballot_sync(0xFFFFFFFFu, fresh[g] && lex_lt(T, (uint32_t)r[g].z & 0x1FFFu, B0k, B0p));
     }
+    int32_t* Gp[SP_U][K];                                               // (address arithmetic off the ballot's shadow)
+#pragma unroll
+    for (int g = 0; g < SP_U; ++g) {
+      const size_t row = (size_t)(uint32_t)(top[g] < 0 ? 0 : top[g]) * (size_t)N;
+#pragma unroll
+      for (int q = 0; q < K; ++q) Gp[g][q] = G + row + (uint32_t)(cn[g][q] < 0 ? 0 : cn[g][q]);
+    }
     int run = 0;
 #pragma unroll
     for (int g = SP_U - 1; g >= 0; --g) run = (okm[g] == 0xFFFFFFFFu) ? 32 + run : (__ffs(~okm[g]) - 1);
 #pragma unroll
     for (int g = 0; g < SP_U; ++g) {
       if (32 * g + lane < run) {                                        // commit: plan.go:238-245 and the step's outcome
-        const int32_t top = lds32(reca[g] + (uint32_t)(SLP + 2) * 4u);
 #pragma unroll
         for (int q = 0; q < K; ++q)
-          if (have_p) atomicAdd(&G[(size_t)top * N + cn[g][q]], 1);
+          if (have_p) atomicAdd(Gp[g][q], 1);
         // the outcome of an accepted step is "its current nodes in (score, position) order": one byte (0x80 | the
         // ranks) in a dense array - one coalesced store per 32 steps - that k_scatter_stream expands
         srank[i + 32 * g + lane] = (uint8_t)(0x80u | (((uint32_t)r[g].z >> 13) & 0xFFu));
