@@ -364,13 +364,13 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass(DPool pool, int s) {
         while (dec) {
           const int s2 = __ffs(dec) - 1;
           dec &= dec - 1;
-          atomicSub(&counts[s2 * N + n], w_p);        // another state's count: only the owner touches it
+          red_add(&counts[s2 * N + n], -w_p);        // another state's count: only the owner touches it
           t -= w_p;
         }
         if (tk) {
           cd[j] = __dadd_rn(cd[j], wpd);
           t += w_p;
-          atomicAdd(&n2n[(size_t)top * N + n], 1);    // fire-and-forget RED; re-read through L2 (ld.cg)
+          red_add(&n2n[(size_t)top * N + n], 1);    // fire-and-forget RED; re-read through L2 (ld.cg)
           if (same_top) qnext[j] += 1;                // the early load missed this increment
         }
         if (t != tot[j]) {

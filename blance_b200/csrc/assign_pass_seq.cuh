@@ -300,13 +300,13 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s, 
           while (dec) {
             const int s2 = __ffs(dec) - 1;
             dec &= dec - 1;
-            atomicSub(&counts[s2 * N + n], w_p);
+            red_add(&counts[s2 * N + n], -w_p);
             t -= w_p;
           }
           if (tk) {
             cd[j] = __dadd_rn(cd[j], wpd);
             t += w_p;
-            atomicAdd(&n2n[(size_t)top * N + n], 1);
+            red_add(&n2n[(size_t)top * N + n], 1);
           }
           if (t != tot[j]) {
             tot[j] = t;
@@ -625,7 +625,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_assign_pass_seq(DPool pool, int s, 
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (wlane && sw * WT + u * WS + wstep < n_acc) {
-        atomicAdd(&n2n[(size_t)top[u] * N + c[u]], 1);               // plan.go:238-245
+        red_add(&n2n[(size_t)top[u] * N + c[u]], 1);               // plan.go:238-245
         int32_t* orec = ostream + (size_t)jst[u] * REC;
         orec[rank[u]] = c[u];                                      // ordered by (score, position)
         if (wq == 0) orec[k] = k;

@@ -56,6 +56,12 @@ namespace blance_dev {
 #define SP_IDLE_NS 500       // a scout with nothing to do sleeps this long between looks at the leader's words
 #define SP_BUSY_NS 100
 #endif
+#ifndef SP_PINF
+#define SP_PINF 1
+#endif
+#ifndef SP_SCAN2
+#define SP_SCAN2 1
+#endif
 #ifndef SP_LB
 #define SP_LB 512            // launch bound (the register budget follows from it: 544 -> 96, 512 -> 128, 384 -> 168)
 #endif
@@ -195,7 +201,10 @@ __global__ void __launch_bounds__(SP_LB, 1) k_assign_pass_spec(DPool pool, int s
   const uint32_t sbit_a = ctl_a + (uint32_t)offsetof(SpecCtl, slot_bit);
   const uint32_t mbar_a = ctl_a + (uint32_t)offsetof(SpecCtl, mbar);
   const uint32_t epoch_a = ctl_a + (uint32_t)offsetof(SpecCtl, epoch);
-  const uint32_t front_a = ctl_a + (uint32_t)offsetof(SpecCtl, front);
+  uint32_t front_a = ctl_a + (uint32_t)offsetof(SpecCtl, front);
+#if SP_PINF
+  asm volatile("" : "+r"(front_a));        // (ptxas otherwise rebuilds it from SR_CgaCtaId - an S2R - for every store of the front)
+#endif
   const uint32_t seq_a = ctl_a + (uint32_t)offsetof(SpecCtl, cmd_seq);
 
   // ---- pass constants, mirror, ring ------------------------------------------------------------------
@@ -389,10 +398,10 @@ __global__ void __launch_bounds__(SP_LB, 1) k_assign_pass_spec(DPool pool, int s
               const int n = team_node(j);
               const bool is_cur = (memb[j] >> s) & 1u, tk = (taken_bits >> j) & 1u;
               if (n < N && (is_cur || tk)) {
-                if (tk) atomicAdd(&G[(size_t)top * N + n], 1);
+                if (tk) red_add(&G[(size_t)top * N + n], 1);
                 if (changed) {
                   const int dA = (tk ? 1 : 0) - ((elig && is_cur) ? 1 : 0);
-                  if (dA) atomicAdd(&A[(size_t)top * N + n], dA);
+                  if (dA) red_add(&A[(size_t)top * N + n], dA);
                   double* nd = reinterpret_cast<double*>(dyn_smem) + 4 * (size_t)n;
                   double cd = nd[0];
                   int32_t t0 = lds32(tot_a + 4u * n), t = t0;
@@ -402,7 +411,7 @@ __global__ void __launch_bounds__(SP_LB, 1) k_assign_pass_spec(DPool pool, int s
                   while (dec) {
                     const int s2 = __ffs(dec) - 1;
                     dec &= dec - 1;
-                    atomicSub(&counts[s2 * N + n], w_p);
+                    red_add(&counts[s2 * N + n], -w_p);
                     t -= w_p;
                   }
                   if (tk) { cd = __dadd_rn(cd, wpd); t += w_p; }
@@ -669,7 +678,12 @@ __global__ void __launch_bounds__(SP_LB, 1) k_assign_pass_spec(DPool pool, int s
 #pragma unroll
       for (int q = 0; q < K; ++q) fresh[g] = fresh[g] && lc[q] <= r[g].w;
       const unsigned long long T = ((unsigned long long)(uint32_t)r[g].x << 32) | (uint32_t)r[g].y;
+#if SP_SCAN2
+      const bool below = lex_lt(T, (uint32_t)r[g].z & 0x1FFFu, B0k, B0p);            // (no short circuit: no branch)
+      okm[g] = __ballot_sync(0xFFFFFFFFu, (int)fresh[g] & (int)below);
+#else
       okm[g] = __ballot_sync(0xFFFFFFFFu, fresh[g] && lex_lt(T, (uint32_t)r[g].z & 0x1FFFu, B0k, B0p));
+#endif
     }
     int32_t* Gp[SP_U][K];                                               // (address arithmetic off the ballot's shadow)
 #pragma unroll
@@ -680,13 +694,19 @@ __global__ void __launch_bounds__(SP_LB, 1) k_assign_pass_spec(DPool pool, int s
     }
     int run = 0;
 #pragma unroll
+#if SP_SCAN2
+    // trailing ones of the mask = the leading run (popc on the integer pipe; ffs is a bit reverse + find-leading-one
+    // on the slow pipe, and needs the all-ones case apart)
+    for (int g = SP_U - 1; g >= 0; --g) run = __popc(okm[g] & ~(okm[g] + 1u)) + (okm[g] == 0xFFFFFFFFu ? run : 0);
+#else
     for (int g = SP_U - 1; g >= 0; --g) run = (okm[g] == 0xFFFFFFFFu) ? 32 + run : (__ffs(~okm[g]) - 1);
+#endif
 #pragma unroll
     for (int g = 0; g < SP_U; ++g) {
       if (32 * g + lane < run) {                                        // commit: plan.go:238-245 and the step's outcome
 #pragma unroll
         for (int q = 0; q < K; ++q)
-          if (have_p) atomicAdd(Gp[g][q], 1);
+          if (have_p) red_add(Gp[g][q], 1);
         // the outcome of an accepted step is "its current nodes in (score, position) order": one byte (0x80 | the
         // ranks) in a dense array - one coalesced store per 32 steps - that k_scatter_stream expands
         srank[i + 32 * g + lane] = (uint8_t)(0x80u | (((uint32_t)r[g].z >> 13) & 0xFFu));
@@ -837,7 +857,7 @@ __global__ void __launch_bounds__(SP_LB, 1) k_assign_pass_spec(DPool pool, int s
           int32_t mine = chosen[0];
 #pragma unroll
           for (int t = 1; t < K; ++t) if (lane == t) mine = chosen[t];
-          atomicAdd(&G[(size_t)top * N + mine], 1);                    // plan.go:238-245
+          red_add(&G[(size_t)top * N + mine], 1);                      // plan.go:238-245
         }
         if (!same) {
           // ---- a mover: lanes 0..n_cur-1 take the old nodes, lanes 8..8+n_ch-1 the new ones -------------------------
@@ -875,7 +895,7 @@ __global__ void __launch_bounds__(SP_LB, 1) k_assign_pass_spec(DPool pool, int s
           unsigned long long nk = ~0ull;
           bool ins = false;
           if (act) {
-            if (have_p && dA) atomicAdd(&A[(size_t)top * N + x], dA);
+            if (have_p && dA) red_add(&A[(size_t)top * N + x], dA);
             const int4 ma = lds128(nd_a + (uint32_t)x * 32u), mb = lds128(nd_a + (uint32_t)x * 32u + 16u);
             const uint32_t fl = dyn_smem[(flg_a - base_a) + x];
             double cd = __hiloint2double(ma.y, ma.x), ff = __hiloint2double(ma.w, ma.z);
@@ -884,7 +904,7 @@ __global__ void __launch_bounds__(SP_LB, 1) k_assign_pass_spec(DPool pool, int s
             while (memb) {
               const int s2 = __ffs(memb) - 1;
               memb &= memb - 1;
-              atomicSub(&counts[s2 * N + x], w_p);
+              red_add(&counts[s2 * N + x], -w_p);
               t -= w_p;
             }
             if (t != t0) {
