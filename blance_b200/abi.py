@@ -34,7 +34,7 @@ class _PlanOut(ctypes.Structure):
 
 
 _CAPI = None
-EXPORTS = ("blance_ctx_create", "blance_ctx_create_multi", "blance_ctx_device_count", "blance_ctx_destroy", "blance_last_error", "blance_version", "blance_ctx_kernel_launches", "blance_plan_next_map",
+EXPORTS = ("blance_ctx_create", "blance_ctx_create_multi", "blance_ctx_device_count", "blance_ctx_destroy", "blance_last_error", "blance_version", "blance_ctx_kernel_launches", "blance_plan_in_check", "blance_plan_next_map",
            "blance_plan_next_map_batch", "blance_plan_upload", "blance_plan_run", "blance_plan_fetch", "blance_plan_free", "blance_plan_timing",
            "blance_calc_partition_moves", "blance_moves_create", "blance_moves_fetch", "blance_moves_available", "blance_moves_free")
 
@@ -54,6 +54,7 @@ def capi():
         lib.blance_last_error.restype = ctypes.c_char_p
         lib.blance_ctx_kernel_launches.argtypes = [vp]
         lib.blance_ctx_kernel_launches.restype = ctypes.c_int64
+        lib.blance_plan_in_check.argtypes = [vp, ctypes.c_char_p, i32]
         lib.blance_plan_next_map.argtypes = [vp, vp, vp]
         lib.blance_plan_next_map_batch.argtypes = [vp, i32, vp, vp]
         lib.blance_plan_upload.argtypes = [vp, vp, ctypes.POINTER(vp)]

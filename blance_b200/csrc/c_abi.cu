@@ -200,11 +200,11 @@ struct blance_plan {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static int validate(blance_ctx* ctx, const blance_plan_in* in, int idx) {
-  char b[256];
+// sizes, pointers and limits of one instance (no table contents: those are blance_plan_in_check's)
+static int check_structure(const blance_plan_in* in, std::string& why) {
   auto bad = [&](const char* what, int st = BLANCE_ERR_INVALID_ARG) {
-    std::snprintf(b, sizeof b, "instance %d: %s", idx, what);
-    return fail(ctx, st, b);
+    why = what;
+    return st;
   };
   if (!in) return bad("plan_in is NULL");
   if (in->n_nodes < 0 || in->n_node_ids < in->n_nodes || in->n_states < 0 || in->n_parts < 0 || in->n_slots < 0)
@@ -244,6 +244,80 @@ static int validate(blance_ctx* ctx, const blance_plan_in* in, int idx) {
   if (in->booster_kind != BLANCE_BOOSTER_NONE && in->booster_kind != BLANCE_BOOSTER_CBGT_MAX)
     return bad("unknown booster_kind", BLANCE_ERR_UNSUPPORTED);
   return BLANCE_OK;
+}
+
+static int validate(blance_ctx* ctx, const blance_plan_in* in, int idx) {
+  std::string why;
+  const int st = check_structure(in, why);
+  if (st == BLANCE_OK) return st;
+  char b[256];
+  std::snprintf(b, sizeof b, "instance %d: %s", idx, why.c_str());
+  return fail(ctx, st, b);
+}
+
+/* The contents of the tables, for bindings that do not trust their own marshalling (the planning entry points
+ * check sizes, pointers and limits only: a scan of every row would sit in the timed path of every call). */
+extern "C" int blance_plan_in_check(const blance_plan_in* in, char* msg, int32_t msg_cap) {
+  std::string why;
+  auto done = [&](int st) {
+    if (msg && msg_cap > 0) std::snprintf(msg, (size_t)msg_cap, "%s", why.c_str());
+    return st;
+  };
+  int st = check_structure(in, why);
+  if (st != BLANCE_OK) return done(st);
+  auto bad = [&](const std::string& what, int code = BLANCE_ERR_INVALID_ARG) { why = what; return done(code); };
+  if (in->n_states > 0 && in->state_slot_off[0] != 0) return bad("state_slot_off[0] != 0");
+  const long long P = in->n_parts, SL = in->n_slots, S = in->n_states;
+  for (int which = 0; which < 2; ++which) {
+    const int32_t* rows = which ? in->cur_rows : in->prev_rows;
+    const uint8_t* shape = which ? in->cur_shape : in->prev_shape;
+    const char* name = which ? "cur" : "prev";
+    int32_t lo = 0, hi = -1;
+    for (long long i = 0; i < P * SL; ++i) { lo = std::min(lo, rows[i]); hi = std::max(hi, rows[i]); }
+    if (lo < BLANCE_NO_NODE || hi >= in->n_node_ids)
+      return bad(std::string(name) + "_rows holds a node id outside [-1, n_node_ids)");
+    uint8_t sh = 0;
+    for (long long i = 0; i < P * S; ++i) sh = std::max(sh, shape[i]);
+    if (sh > BLANCE_SHAPE_LIST) return bad(std::string(name) + "_shape holds a value above BLANCE_SHAPE_LIST");
+    // a state's list is filled from the left: no node after an empty slot
+    for (long long p = 0; p < P; ++p)
+      for (int s = 0; s < in->n_states; ++s) {
+        bool gap = false;
+        for (int c = in->state_slot_off[s]; c < in->state_slot_off[s + 1]; ++c) {
+          const int32_t x = rows[p * SL + c];
+          if (x == BLANCE_NO_NODE) gap = true;
+          else if (gap) return bad(std::string(name) + "_rows: partition " + std::to_string(p) + " has a node after an empty slot of state " + std::to_string(s));
+        }
+      }
+  }
+  {
+    // part_name_rank: 0 <= rank < 2^30, unique (it is the last word of the partition sort key, plan.go:512-528)
+    std::vector<uint64_t> seen;
+    std::vector<int32_t> big;
+    seen.assign((size_t)((P + 63) / 64), 0);
+    for (long long p = 0; p < P; ++p) {
+      const int32_t r = in->part_name_rank[p];
+      if (r < 0 || r >= (1 << 30)) return bad("part_name_rank outside [0, 2^30) at partition " + std::to_string(p));
+      if (r < P) {
+        if (seen[(size_t)(r >> 6)] >> (r & 63) & 1ull) return bad("part_name_rank " + std::to_string(r) + " appears twice");
+        seen[(size_t)(r >> 6)] |= 1ull << (r & 63);
+      } else big.push_back(r);
+    }
+    std::sort(big.begin(), big.end());
+    if (std::adjacent_find(big.begin(), big.end()) != big.end()) return bad("a part_name_rank appears twice");
+    // the weight word of the key is 999999999 - w printed with %10d (plan.go:539): beyond 999999999 the reference's
+    // STRING order and a numeric order part ways
+    for (long long p = 0; p < P; ++p)
+      if (in->has_part_weights && in->part_has_weight[p] && in->part_weight[p] > 999999999)
+        return bad("partition weight above 999999999 at partition " + std::to_string(p), BLANCE_ERR_UNSUPPORTED);
+  }
+  if (in->has_hier_rules)
+    for (int s = 0; s <= in->n_states; ++s) {
+      if (in->rule_off[s] < 0 || in->rule_off[s] > in->n_rules || (s > 0 && in->rule_off[s] < in->rule_off[s - 1]))
+        return bad("rule_off is not a monotone offset table into the rules");
+    }
+  why.clear();
+  return done(BLANCE_OK);
 }
 
 static void plan_release(blance_plan* pl, blance_ctx* ctx = nullptr) {

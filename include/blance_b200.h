@@ -160,6 +160,15 @@ typedef struct blance_plan_out {
   int64_t sticky_steps;    /* of `steps`: accepted scout results / sequencer-window steps (no full evaluation) */
 } blance_plan_out;
 
+/* Checks one instance's tables without planning anything and without a device: sizes, pointers and limits (what
+ * every planning entry point checks itself) AND the contents - state_slot_off[0] == 0, node ids of both row tables
+ * in [-1, n_node_ids), each state's slots filled from the left, shape values, part_name_rank unique and below
+ * 2^30, partition weights within the "%10d" rule of plan.go:539, rule_off monotone.  The planning entry points do
+ * NOT scan the contents (it would sit in the timed path of every call): a binding that does not trust its own
+ * marshalling calls this first.  Returns BLANCE_OK / BLANCE_ERR_INVALID_ARG / BLANCE_ERR_UNSUPPORTED; msg (may be
+ * NULL) receives the reason, truncated to msg_cap bytes. */
+int blance_plan_in_check(const blance_plan_in* in, char* msg, int32_t msg_cap);
+
 /* Host buffers in, host buffers out.  If prevMap and partitionsToAssign must be
  * mutated as plan.go:49-52 does, the caller copies next_rows back when
  * iters_run >= 2 || !converged. */
