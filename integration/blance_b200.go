@@ -42,6 +42,9 @@ var (
 	b200Ctx  *C.blance_ctx
 )
 
+// b200CheckTables makes every plan run blance_plan_in_check on its tables first (set it in the shim's own tests).
+var b200CheckTables = false
+
 func b200() *C.blance_ctx {
 	b200Once.Do(func() {
 		if st := C.blance_ctx_create(&b200Ctx, -1); st != C.BLANCE_OK {
@@ -426,6 +429,14 @@ func planNextMapExB200(prevMap, partitionsToAssign PartitionMap,
 	pWarn, warn := ar.u8(PU * S)
 	out.next_rows, out.next_shape, out.warn = pNext, pNextShape, pWarn
 
+	if b200CheckTables { // development aid: the planning call itself does not scan every cell
+		var msg [256]C.char
+		if st := C.blance_plan_in_check(&in, &msg[0], 256); st == C.BLANCE_ERR_UNSUPPORTED {
+			return planNextMapEx(prevMap, partitionsToAssign, nodesAll, nodesToRemove, nodesToAdd, model, opts)
+		} else if st != C.BLANCE_OK {
+			panic("blance_b200: malformed tables: " + C.GoString(&msg[0]))
+		}
+	}
 	if st := C.blance_plan_next_map(b200(), &in, &out); st != C.BLANCE_OK {
 		if st == C.BLANCE_ERR_UNSUPPORTED || st == C.BLANCE_ERR_CUDA || st == C.BLANCE_ERR_NOMEM {
 			// nothing was mutated yet: the Go planner answers (same results, only slower)
